@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- cavity-force + Bussi step throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one 1M-particle (+1 photon) synthetic charged box:
+the cavity force (cavb200_force: dipole reduce + per-particle force + photon force + energies) and
+the BussiReservoir thermostat (cavb200_bussi: KE reduce + alpha + velocity rescale), i.e. the two
+calls HOOMD's integrator makes into the plugin per step.  Prints ONE JSON line (rank 0).
+
+  value      M particle-steps/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the host-buffer C-ABI call cavb200_step_host: pinned host arrays
+             in, host arrays out, H2D/D2H inside the timed region
+  roofline   dominant kernel (the cavity-force kernel): algorithmic 84 B/particle / its own
+             CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own CPU code (oracle/_ref: src/CavityForceCompute.cc +
+             src/BussiReservoirThermostat.h compiled verbatim) on the host cores, bounded sample
+
+L2 hygiene: the timed loop rotates over `--systems` distinct systems (default 8 x 116 MB = 928 MB,
+larger than the 126 MB L2), so no step finds its inputs in L2.
+
+N > 1 (torchrun, one process per GPU): every rank runs an independent replica (BASELINE config 3,
+no data-path collective; "scaling": "weak"); rank 0 reports the aggregate.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cav_hoomd_b200 import synth  # noqa: E402
+
+METRIC = "cavity-force+Bussi M particle-steps/s"
+UNIT = "M particle-steps/s"
+OMEGAC, COUPLSTR, PHMASS = 0.01, 1e-3, 1.0
+FORCE_BYTES, BUSSI_BYTES = 84, 64  # algorithmic bytes per particle
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU code on the host cores
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One replica, one thread: `steps` x (reference cavity force + reference Bussi step)."""
+    n_mol, replica, steps, kind = args
+    from oracle import oracle as O
+    s = synth.make_system(n_mol, replica=replica)
+    rng = np.random.default_rng(replica)
+    dof = 3.0 * n_mol - 3.0
+    draws = [(rng.standard_normal(), rng.gamma((dof - 1) / 2)) for _ in range(steps)]
+    if kind == "reference":
+        ro = O.RefOracle()
+        hc = ro.cavity_open(s.N, s.box, s.L_typeid, OMEGAC, COUPLSTR, PHMASS)
+        ro.lib.ref_cavity_load(hc, O._d(s.pos), O._d(s.charge), O._i(s.image))
+        hb = ro.bussi_open(s.vel, np.arange(n_mol, dtype=np.uint32), dof, synth.KT_100K, synth.TAU_5PS)
+        ro.lib.ref_cavity_compute(hc, 1)  # warm-up (page faults)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            ro.lib.ref_cavity_compute(hc, 1)
+            ro.bussi_step(hb, k, synth.DT_1FS, draws[k][0], draws[k][1])
+        dt = time.perf_counter() - t0
+    else:
+        co = O.COracle()
+        idx = np.arange(n_mol, dtype=np.uint32)
+        res = np.zeros(2)
+        co.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, OMEGAC, COUPLSTR, PHMASS)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            co.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, OMEGAC, COUPLSTR, PHMASS)
+            co.bussi_step(s.vel, idx, dof, synth.DT_1FS, synth.KT_100K, synth.TAU_5PS, draws[k][0], draws[k][1], res)
+        dt = time.perf_counter() - t0
+    return s.N * steps, dt
+
+
+def cpu_reference_throughput(n_mol: int, steps: int, cores: int):
+    """Aggregate M particle-steps/s of `cores` concurrent single-threaded replicas (the reference CPU
+    path is single-threaded; its authors run one core per replica, reference submit.sh:7)."""
+    import multiprocessing as mp
+    from oracle import oracle as O
+    O.build()
+    kind = "reference" if O.have_ref() else "port"
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(n_mol, r, steps, kind) for r in range(cores)])
+    wall = time.perf_counter() - t0
+    # every worker times only its own compute loop; the job rate is the sum of per-replica rates
+    rate = sum(n / dt for n, dt in res) / 1e6
+    return dict(value=rate, unit=UNIT, cores=cores, kind=kind,
+                sample=f"{cores} concurrent 1-thread replicas x {steps} steps of the {n_mol + 1}-particle box "
+                       f"(cavity force + Bussi), wall {wall:.1f} s incl. setup")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    cores = min(cores, 128)
+    # a reference step of the 1M box is ~40 ms on one core; bound the whole run to a few minutes
+    per_step_s = 0.06
+    steps = max(1, min(args.steps, int(120.0 / per_step_s / 1) // 1))
+    steps = min(steps, 50)
+    t0 = time.perf_counter()
+    out = cpu_reference_throughput(args.n_mol, steps + 0, cores)
+    ms = 1e3 * (args.n_mol + 1) * cores / (out["value"] * 1e6)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": out["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {args.n_mol}-particle charged box + 1 photon, CavityForce g=1e-3 "
+                               f"omegac=0.01 + BussiReservoir kT=100K tau=5ps (BASELINE configs[1])",
+                   "arm": "reference CPU classes on host cores, one replica per core"},
+        "cpu_baseline": out,
+        "e2e": {"value": out["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+class DeviceSystem:
+    """One particle system resident in HBM, HOOMD layouts."""
+
+    def __init__(self, capi, s):
+        self.N = s.N
+        self.box = s.box
+        self.L_typeid = s.L_typeid
+        self.pos = capi.DeviceArray.from_numpy(s.pos)
+        self.charge = capi.DeviceArray.from_numpy(s.charge)
+        self.image = capi.DeviceArray.from_numpy(s.image)
+        self.vel = capi.DeviceArray.from_numpy(s.vel)
+        self.force = capi.DeviceArray((s.N, 4), np.float64)
+
+
+def run_b200(args):
+    from cav_hoomd_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # plumbing only: barrier + max over ranks
+        dist.init_process_group(backend="gloo")
+
+    if capi.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device; the product has no CPU fallback")
+    h = capi.Handle(local_rank)
+    if args.variant is not None:
+        h.set_tuning(variant=args.variant)
+    if args.threads:
+        h.set_tuning(threads=args.threads)
+    if args.ctas_per_sm:
+        h.set_tuning(ctas_per_sm=args.ctas_per_sm)
+    if args.unroll:
+        h.set_tuning(unroll=args.unroll)
+
+    n_mol = args.n_mol
+    base = synth.make_system(n_mol, replica=rank)
+    N = base.N
+    systems = []
+    for k in range(args.systems):
+        s = base if k == 0 else synth.make_system(n_mol, replica=rank + 1000 * k)
+        systems.append(DeviceSystem(capi, s))
+    params = capi.Params.make(OMEGAC, COUPLSTR, PHMASS)
+    dof = 3.0 * n_mol - 3.0
+    rng = np.random.default_rng(1234 + rank)
+    total = args.warmup + 2 * args.steps + 8
+    bargs = [capi.BussiArgs(synth.KT_100K, synth.TAU_5PS, synth.DT_1FS, dof, rng.standard_normal(),
+                            rng.gamma((dof - 1) / 2)) for _ in range(total)]
+    stream = capi.Stream()
+    st = stream.ptr
+
+    def step(k, fused):
+        d = systems[k % len(systems)]
+        if fused:
+            h.step(d.pos, d.charge, d.image, d.force, d.vel, N, d.box, d.L_typeid, params, 0, n_mol, bargs[k], st)
+        else:
+            h.force(d.pos, d.charge, d.image, d.force, N, d.box, d.L_typeid, params, st)
+            h.bussi(d.vel, None, 0, n_mol, bargs[k], st)
+
+    def barrier():
+        capi.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def timed(fused, steps, k0):
+        e0, e1 = capi.Event(), capi.Event()
+        barrier()
+        l0 = h.launch_count
+        e0.record(st)
+        for k in range(steps):
+            step(k0 + k, fused)
+        e1.record(st)
+        ms = e1.elapsed_ms_since(e0)
+        capi.sync()
+        launches = h.launch_count - l0
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, launches
+
+    # warm-up (>= 3), both paths
+    for k in range(max(args.warmup, 3)):
+        step(k, False)
+        step(k, True)
+    capi.sync()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_sep, launches = timed(False, args.steps, args.warmup)
+    ms_fused, launches_fused = timed(True, args.steps, args.warmup + args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-kernel durations (dominant kernel = cavity force), CUDA events on the launching stream
+    evs = [(capi.Event(), capi.Event(), capi.Event()) for _ in range(args.steps)]
+    capi.sync()
+    for k in range(args.steps):
+        d = systems[k % len(systems)]
+        a, b, c = evs[k]
+        a.record(st)
+        h.force(d.pos, d.charge, d.image, d.force, N, d.box, d.L_typeid, params, st)
+        b.record(st)
+        h.bussi(d.vel, None, 0, n_mol, bargs[k], st)
+        c.record(st)
+    capi.sync()
+    t_force = float(np.mean([b.elapsed_ms_since(a) for a, b, c in evs]))
+    t_bussi = float(np.mean([c.elapsed_ms_since(b) for a, b, c in evs]))
+
+    # e2e: host-buffer C-ABI call, pinned host arrays, copies inside the timed region
+    e2e_steps = max(3, min(args.steps, 20))
+    pin = {k: capi.PinnedArray.from_numpy(getattr(base, k)) for k in ("pos", "charge", "image", "vel")}
+    pin_force = capi.PinnedArray((N, 4), np.float64)
+    for k in range(2):
+        h.step_host(pin["pos"], pin["charge"], pin["image"], pin_force, pin["vel"], N, base.box, base.L_typeid, params, 0,
+                    n_mol, bargs[k])
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        en, bo = h.step_host(pin["pos"], pin["charge"], pin["image"], pin_force, pin["vel"], N, base.box, base.L_typeid,
+                             params, 0, n_mol, bargs[k])
+    capi.sync()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * N * e2e_steps / e2e_s / 1e6
+
+    # sanity: the run must have produced finite forces and a sane alpha (not a timing of nothing)
+    en, dip, ph = h.force_read(st)
+    bo = h.bussi_read(st)
+    assert ph == n_mol and np.isfinite(en).all() and bo["err"] == 0.0 and 0.5 < bo["alpha"] < 1.5, (ph, en, bo)
+
+    if rank != 0:
+        return 0
+
+    peak, peak_src = measured_peak()
+    value = world * N * args.steps / (ms_sep * 1e-3) / 1e6
+    value_fused = world * N * args.steps / (ms_fused * 1e-3) / 1e6
+    achieved = FORCE_BYTES * N / (t_force * 1e-3) / 1e9
+    step_gbs = (FORCE_BYTES + BUSSI_BYTES) * N * args.steps / (ms_sep * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_sep / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": f"synthetic {n_mol}-particle charged box + 1 photon, CavityForce g=1e-3 omegac=0.01 + "
+                        f"BussiReservoir kT=100K tau=5ps (BASELINE configs[1])" + (
+                            f"; {world} independent replicas, one per GPU (configs[2])" if world > 1 else ""),
+            "path": "cavb200_force + cavb200_bussi per step (the two plugin calls), device-resident arrays",
+            "l2": f"inputs larger than L2: rotating over {len(systems)} systems x {116 * N / 1e6:.0f} MB",
+            "tuning": {k: h.get_tuning(k) for k in ("variant", "threads", "ctas_per_sm", "unroll")},
+        },
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "cavity force (k_fused<force>)", "algorithmic_bytes_per_particle": FORCE_BYTES,
+            "kernel_ms": t_force, "peak_source": peak_src,
+            "step": {"algorithmic_bytes_per_particle": FORCE_BYTES + BUSSI_BYTES, "achieved": step_gbs / world,
+                     "frac": step_gbs / world / peak},
+            "bussi_kernel": {"kernel_ms": t_bussi, "achieved": BUSSI_BYTES * n_mol / (t_bussi * 1e-3) / 1e9,
+                             "frac": BUSSI_BYTES * n_mol / (t_bussi * 1e-3) / 1e9 / peak},
+        },
+        "fused_step": {"value": value_fused, "unit": UNIT, "ms_per_step": ms_fused / args.steps,
+                       "frac": (FORCE_BYTES + BUSSI_BYTES) * N * args.steps / (ms_fused * 1e-3) / 1e9 / world / peak,
+                       "path": "cavb200_step (one launch for force + Bussi)", "gpu_launches": launches_fused},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 52 * N + 32 * n_mol,
+                "d2h_bytes_per_step": 32 * N + 32 * n_mol + 160, "steps": e2e_steps,
+                "path": "cavb200_step_host, pinned host buffers"},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = min(os.cpu_count() or 1, 32)
+        line["cpu_baseline"] = cpu_reference_throughput(n_mol, args.cpu_steps, cores)
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-mol", type=int, default=1_000_000)
+    ap.add_argument("--systems", type=int, default=8)
+    ap.add_argument("--variant", type=int, default=None)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--unroll", type=int, default=0)
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

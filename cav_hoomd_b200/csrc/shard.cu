@@ -1,0 +1,385 @@
+// shard.cu -- particle-sharded multi-GPU step (one process per GPU).
+//
+// New functionality relative to the reference (which sums the dipole over the local getN() only
+// and never reduces across ranks, src/CavityForceCompute.cc:142,166): each rank
+// owns a contiguous block of particles and one 128-byte record per rank crosses NVLink per step:
+//   kernel A  reduce over the local particles; the last CTA merges the CTA records into the
+//             rank's record {d as (hi,lo) pairs, sum m|v|^2, first 'L' (global index, q, term), n_L}
+//   exchange  mode 0: ncclAllGather (libnccl resolved with dlopen, no link-time dependency)
+//             mode 1: the same last CTA stores the record straight into every peer's mailbox
+//                     (CUDA-IPC mapped peer memory over NVLink) and then raises a sequence flag;
+//                     there is no collective call and no host involvement
+//   kernel B  every CTA merges the nranks records in RANK ORDER (deterministic, identical on all
+//             ranks), forms Dq / F_L / energies / alpha, and applies forces and the rescale.
+//             In mode 1 it first spins (bounded) on its own flags.
+// Because d travels as compensated pairs the result differs from the single-GPU one only in the
+// final rounding of hi+lo.
+#include "hotpath.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace cavb
+    {
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v)
+    {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p)
+    {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+    }
+
+struct PeerTable
+    {
+    Partial* mailbox[16];
+    unsigned long long* flags[16];
+    };
+
+// kernel A
+template<int UNROLL>
+__global__ void __launch_bounds__(1024, 1)
+    k_shard_reduce(ForceIn f, BussiIn b, Partial* recs, unsigned long long* ticket, Partial* rank_record, int mode,
+                   int rank, int nranks, unsigned long long seq, PeerTable peers)
+    {
+    __shared__ BlockScratch sc;
+    __shared__ int s_last;
+    reduce_phase<true, true, UNROLL>(f, b, sc);
+    store_record(recs + blockIdx.x, sc.rec);
+    __syncthreads();
+    if (threadIdx.x == 0)
+        {
+        __threadfence();
+        const unsigned long long t = atom_acq_rel_add_u64(ticket, 1ull);
+        s_last = (t == (unsigned long long)gridDim.x - 1);
+        }
+    __syncthreads();
+    if (!s_last)
+        return;
+    merge_phase<true, true>(recs, (int)gridDim.x, sc);
+    if (threadIdx.x == 0)
+        *ticket = 0ull;
+    if (mode == 0)
+        {
+        store_record(rank_record, sc.rec); // ncclAllGather sends it from here
+        return;
+        }
+    // mode 1: one 16-byte word per (peer, word) pair, then one flag per peer
+    const int parity = (int)(seq & 1ull);
+    const double2* src = reinterpret_cast<const double2*>(&sc.rec);
+    for (int e = threadIdx.x; e < nranks * 8; e += blockDim.x)
+        {
+        const int peer = e >> 3, w = e & 7;
+        double2* dst = reinterpret_cast<double2*>(peers.mailbox[peer] + (size_t)parity * 16 + rank);
+        dst[w] = src[w];
+        }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < nranks)
+        st_release_sys_u64(peers.flags[threadIdx.x] + rank, seq);
+    }
+
+// kernel B
+template<int UNROLL>
+__global__ void __launch_bounds__(1024, 1)
+    k_shard_apply(ForceIn f, BussiIn b, const Partial* gathered, Scalars* scalars, int mode, int nranks,
+                  unsigned long long seq, const unsigned long long* my_flags)
+    {
+    __shared__ BlockScratch sc;
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0)
+        s_timeout = 0;
+    __syncthreads();
+    if (mode == 1 && (int)threadIdx.x < nranks)
+        {
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys_u64(my_flags + threadIdx.x) < seq)
+            {
+            if (globaltimer_ns() - t0 > 2000000000ull) // 2 s: never hang the GPU
+                {
+                s_timeout = 1;
+                break;
+                }
+            }
+        }
+    __syncthreads();
+    const int timeout = s_timeout;
+    const Partial* recs = gathered + (mode == 1 ? (size_t)(seq & 1ull) * 16 : 0);
+    combine_phase<true, true>(recs, nranks, f, b, sc, scalars, blockIdx.x == 0, timeout);
+    if (timeout)
+        return;
+    apply_phase<true, true, UNROLL>(sc.fin, f, b);
+    }
+
+// ---- NCCL through dlopen ----------------------------------------------------------------------
+struct NcclApi
+    {
+    void* lib;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    };
+
+static NcclApi* nccl_api()
+    {
+    static NcclApi api = {};
+    static int tried = 0;
+    if (!tried)
+        {
+        tried = 1;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (int i = 0; i < 2 && !api.lib; i++)
+            api.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib)
+            {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+            api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+            if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy)
+                api.lib = nullptr;
+            }
+        }
+    return api.lib ? &api : nullptr;
+    }
+
+static int ensure_mailbox(cavb200_handle* h)
+    {
+    ShardState& sh = h->shard;
+    if (sh.mailbox_alloc)
+        return 0;
+    // [2 parities][16 ranks] records + [16] flags, zeroed
+    const size_t bytes = sizeof(Partial) * 32 + sizeof(unsigned long long) * 16;
+    CAVB_CHECK(cudaMalloc(&sh.mailbox_alloc, bytes));
+    CAVB_CHECK(cudaMemset(sh.mailbox_alloc, 0, bytes));
+    sh.gather = reinterpret_cast<Partial*>(sh.mailbox_alloc);
+    sh.flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(sh.mailbox_alloc) + sizeof(Partial) * 32);
+    sh.peer_mailbox[0] = sh.gather;
+    sh.peer_flags[0] = sh.flags;
+    return 0;
+    }
+
+template<int UNROLL> static int launch_shard_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaStream_t s)
+    {
+    ShardState& sh = h->shard;
+    int rc = ensure_mailbox(h);
+    if (rc)
+        return rc;
+    const int threads = h->tune.threads;
+    const unsigned long long work = f.N > b.n ? f.N : b.n;
+    unsigned long long want = (work + threads - 1) / threads;
+    if (want < 1)
+        want = 1;
+    int max_grid = h->num_sms * h->tune.ctas_per_sm;
+    if (max_grid > MAX_PARTIALS)
+        max_grid = MAX_PARTIALS;
+    const int grid = (int)(want < (unsigned long long)max_grid ? want : (unsigned long long)max_grid);
+    sh.seq += 1;
+    PeerTable peers;
+    for (int r = 0; r < 16; r++)
+        {
+        peers.mailbox[r] = sh.peer_mailbox[r];
+        peers.flags[r] = sh.peer_flags[r];
+        }
+    const int nranks = sh.nranks < 1 ? 1 : sh.nranks;
+    const int mode = (nranks == 1 && sh.mode == 0) ? 1 : sh.mode; // one rank: the mailbox path is local
+    if (nranks == 1)
+        {
+        peers.mailbox[0] = sh.gather;
+        peers.flags[0] = sh.flags;
+        }
+    Partial* rank_record = h->partials + MAX_PARTIALS - 1;
+    k_shard_reduce<UNROLL><<<grid, threads, 0, s>>>(f, b, h->partials, h->counters + 4, rank_record, mode, sh.rank, nranks,
+                                                     sh.seq, peers);
+    CAVB_CHECK(cudaGetLastError());
+    if (mode == 0)
+        {
+        NcclApi* api = nccl_api();
+        if (!api || !sh.nccl_comm)
+            return (int)cudaErrorNotReady;
+        if (api->AllGather(rank_record, sh.gather, sizeof(Partial), ncclChar, (ncclComm_t)sh.nccl_comm, s) != ncclSuccess)
+            return (int)cudaErrorUnknown;
+        }
+    k_shard_apply<UNROLL><<<grid, threads, 0, s>>>(f, b, sh.gather, h->scalars, mode, nranks, sh.seq, sh.flags);
+    CAVB_CHECK(cudaGetLastError());
+    h->launches += 2;
+    return 0;
+    }
+
+int launch_shard_step(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cudaStream_t s)
+    {
+    switch (h->tune.unroll)
+        {
+    case 1:
+        return launch_shard_t<1>(h, *f, *b, s);
+    case 4:
+        return launch_shard_t<4>(h, *f, *b, s);
+    default:
+        return launch_shard_t<2>(h, *f, *b, s);
+        }
+    }
+    } // namespace cavb
+
+using namespace cavb;
+
+void cavb_shard_release(cavb200_handle* h)
+    {
+    ShardState& sh = h->shard;
+    for (int r = 0; r < 16; r++)
+        if (r != sh.rank && sh.peer_mailbox[r] && sh.nranks > 1)
+            cudaIpcCloseMemHandle(sh.peer_mailbox[r]);
+    if (sh.nccl_comm)
+        {
+        NcclApi* api = nccl_api();
+        if (api)
+            api->CommDestroy((ncclComm_t)sh.nccl_comm);
+        }
+    cudaFree(sh.mailbox_alloc);
+    memset(&sh, 0, sizeof(sh));
+    }
+
+extern "C"
+    {
+int cavb200_shard_nccl_unique_id(void* out128)
+    {
+    if (!out128)
+        return (int)cudaErrorInvalidValue;
+    NcclApi* api = nccl_api();
+    if (!api)
+        return (int)cudaErrorSharedObjectInitFailed;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == CAVB200_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    if (api->GetUniqueId(&id) != ncclSuccess)
+        return (int)cudaErrorUnknown;
+    memcpy(out128, &id, sizeof(id));
+    return 0;
+    }
+
+int cavb200_shard_init_nccl(cavb200_handle* h, const void* unique_id128, int rank, int nranks)
+    {
+    if (!h || !unique_id128 || nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks)
+        return (int)cudaErrorInvalidValue;
+    NcclApi* api = nccl_api();
+    if (!api)
+        return (int)cudaErrorSharedObjectInitFailed;
+    CAVB_CHECK(cudaSetDevice(h->device));
+    int rc = ensure_mailbox(h);
+    if (rc)
+        return rc;
+    ncclUniqueId id;
+    memcpy(&id, unique_id128, sizeof(id));
+    ncclComm_t comm;
+    if (api->CommInitRank(&comm, nranks, id, rank) != ncclSuccess)
+        return (int)cudaErrorUnknown;
+    h->shard.nccl_comm = comm;
+    h->shard.rank = rank;
+    h->shard.nranks = nranks;
+    h->shard.mode = 0;
+    return 0;
+    }
+
+int cavb200_shard_mailbox_export(cavb200_handle* h, void* out64)
+    {
+    if (!h || !out64)
+        return (int)cudaErrorInvalidValue;
+    CAVB_CHECK(cudaSetDevice(h->device));
+    int rc = ensure_mailbox(h);
+    if (rc)
+        return rc;
+    cudaIpcMemHandle_t mh;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    CAVB_CHECK(cudaIpcGetMemHandle(&mh, h->shard.mailbox_alloc));
+    memcpy(out64, &mh, sizeof(mh));
+    return 0;
+    }
+
+int cavb200_shard_mailbox_open(cavb200_handle* h, const void* handles, int rank, int nranks)
+    {
+    if (!h || !handles || nranks < 1 || nranks > 16 || rank < 0 || rank >= nranks)
+        return (int)cudaErrorInvalidValue;
+    CAVB_CHECK(cudaSetDevice(h->device));
+    int rc = ensure_mailbox(h);
+    if (rc)
+        return rc;
+    ShardState& sh = h->shard;
+    for (int r = 0; r < nranks; r++)
+        {
+        void* base = nullptr;
+        if (r == rank)
+            base = sh.mailbox_alloc;
+        else
+            {
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, (const char*)handles + 64 * r, sizeof(mh));
+            CAVB_CHECK(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+            }
+        sh.peer_mailbox[r] = reinterpret_cast<Partial*>(base);
+        sh.peer_flags[r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + sizeof(Partial) * 32);
+        }
+    sh.rank = rank;
+    sh.nranks = nranks;
+    sh.mode = 1;
+    return 0;
+    }
+
+int cavb200_shard_set_mode(cavb200_handle* h, int mode)
+    {
+    if (!h || (mode != 0 && mode != 1))
+        return (int)cudaErrorInvalidValue;
+    if (mode == 0 && h->shard.nranks > 1 && !h->shard.nccl_comm)
+        return (int)cudaErrorNotReady;
+    if (mode == 1 && h->shard.nranks > 1 && !h->shard.peer_mailbox[(h->shard.rank + 1) % h->shard.nranks])
+        return (int)cudaErrorNotReady;
+    h->shard.mode = mode;
+    return 0;
+    }
+
+int cavb200_shard_step(cavb200_handle* h, const double* pos, const double* charge, const int32_t* image, double* force,
+                       double* vel, uint32_t N_local, uint64_t index_offset, double Lx, double Ly, double Lz,
+                       uint32_t L_typeid, const cavb200_params* params, uint32_t group_first, uint32_t n_group,
+                       const cavb200_bussi_args* bussi, void* stream)
+    {
+    if (!h || !params || !bussi)
+        return (int)cudaErrorInvalidValue;
+    if ((unsigned long long)group_first + n_group > N_local)
+        return (int)cudaErrorInvalidValue;
+    // every rank must take part in the exchange even with an empty shard, so no N == 0 shortcut
+    if (N_local > 0 && (!pos || !charge || !image || !force))
+        return (int)cudaErrorInvalidValue;
+    if (n_group > 0 && !vel)
+        return (int)cudaErrorInvalidValue;
+    if ((reinterpret_cast<uintptr_t>(pos) & 31) || (reinterpret_cast<uintptr_t>(force) & 31)
+        || (reinterpret_cast<uintptr_t>(vel) & 31))
+        return (int)cudaErrorMisalignedAddress;
+    ForceIn f;
+    f.pos = reinterpret_cast<const double4*>(pos);
+    f.charge = charge;
+    f.image = image;
+    f.force = reinterpret_cast<double4*>(force);
+    f.N = N_local;
+    f.index_offset = index_offset;
+    f.Lx = Lx;
+    f.Ly = Ly;
+    f.Lz = Lz;
+    f.L_typeid = L_typeid;
+    f.g = params->couplstr;
+    f.K = params->K;
+    BussiIn b;
+    b.vel = reinterpret_cast<double4*>(vel);
+    b.gidx = nullptr;
+    b.first = group_first;
+    b.n = n_group;
+    b.rescale = bussi->deltaT != 0.0;
+    b.kT = bussi->kT;
+    b.dof = bussi->dof;
+    b.r_normal = bussi->r_normal;
+    b.c = (bussi->tau != 0.0) ? exp(-bussi->deltaT / bussi->tau) : 0.0;
+    b.r_gamma = (bussi->dof > 1.0) ? 2.0 * bussi->gamma_draw : 0.0;
+    return launch_shard_step(h, &f, &b, (cudaStream_t)stream);
+    }
+    }

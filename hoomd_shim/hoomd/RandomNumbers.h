@@ -1,0 +1,2 @@
+// hoomd_shim/hoomd/RandomNumbers.h -- forwards to the single shim header (see ShimCore.h for what this is).
+#include "ShimCore.h"

@@ -1,0 +1,216 @@
+/*
+ * cavb200.h -- C ABI of libcavb200.so, the B200 (sm_100a) implementation of cav-hoomd's
+ * data-parallel hot path: the cavity force, the BussiReservoir kinetic-energy reduce + velocity
+ * rescale, and the F(k,t) density-field sum.
+ *
+ * This is the drop-in boundary.  The reference's plugin layer calls ONE C++ driver,
+ *     hipError_t hoomd::cavitymd::kernel::gpu_compute_cavity_force(Scalar4* d_force,
+ *         const Scalar4* d_pos, const Scalar* d_charge, const int3* d_image, const BoxDim* box,
+ *         unsigned N, const cavity_force_params&, Scalar* d_temp_energy, int* d_photon_idx,
+ *         Scalar3* d_temp_dipole, Scalar3* d_dipole_global, unsigned L_typeid, unsigned& block_size)
+ *     (reference src/CavityForceComputeGPU.cuh:28-40, called from src/CavityForceComputeGPU.cc:172-184)
+ * and gets the kinetic energy / velocity rescale from HOOMD itself
+ *     (reference src/BussiReservoirThermostat.h:50-55 and :78-98).
+ * Each entry point below names the reference interface it replaces.  plugin/ holds the
+ * pybind11/HOOMD host classes that bind to this header; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C types only.  Particle arrays use HOOMD's device layouts and are BORROWED for the
+ *     duration of the call (the library never frees or retains them):
+ *         pos    double[4*N]  x,y,z,w   w = type id in the LOW 32 bits   (Scalar4, 32-byte aligned)
+ *         vel    double[4*N]  vx,vy,vz,mass                              (Scalar4, 32-byte aligned)
+ *         force  double[4*N]  fx,fy,fz,pe                                (Scalar4, 32-byte aligned)
+ *         charge double[N]                                               (8-byte aligned)
+ *         image  int32[3*N]                                              (int3, 4-byte aligned)
+ *   - every compute call is ASYNCHRONOUS on `stream` (a cudaStream_t passed as void*; NULL is the
+ *     legacy default stream HOOMD runs on) and never synchronises the host.  Scalars (energies,
+ *     dipole, KE, alpha) stay on the device until a *_read call copies them back.
+ *   - return value: a cudaError_t as int (0 = success).  NULL array arguments with N > 0 return
+ *     cudaErrorInvalidValue (1), like the reference driver (CavityForceComputeGPU.cu:522-528);
+ *     N == 0 is a successful no-op (:530-532).  There is no CPU fallback anywhere: without a
+ *     CUDA device cavb200_create fails.
+ *   - a handle owns its workspace and is bound to one device; calls on one handle must be issued
+ *     from one host thread at a time (HOOMD's integrator thread).
+ */
+#ifndef CAVB200_H
+#define CAVB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAVB200_VERSION 100
+
+typedef struct cavb200_handle cavb200_handle;
+
+/* Mirrors struct cavity_force_params {omegac, couplstr, K, phmass}
+ * (reference src/CavityForceCompute.h:28-54).  K = phmass*omegac*omegac is filled by the caller
+ * exactly as the reference constructor does (:38-42). */
+typedef struct
+    {
+    double omegac;
+    double couplstr;
+    double K;
+    double phmass;
+    } cavb200_params;
+
+/* Everything compute_rescale_factor needs that does NOT depend on the kinetic energy
+ * (reference src/BussiReservoirThermostat.h:177-225): the two random draws are made by the host
+ * class (HOOMD's RandomGenerator in a real build) BEFORE the launch, so the factor can be formed
+ * on the device right after the reduction with no host round trip.
+ *   r_normal   = normal(rng)                        (:192-193)
+ *   gamma_draw = gamma((dof-1)/2, 1)(rng) if dof>1  (:195-200; the library doubles it like :199) */
+typedef struct
+    {
+    double kT;         /* set_T, the temperature set point at this timestep (:69) */
+    double tau;        /* thermostat time constant; 0 = instantaneous (:186-190) */
+    double deltaT;     /* step size; 0 makes the call a no-op with alpha = 1 (:45-48) */
+    double dof;        /* translational degrees of freedom of the group (:52) */
+    double r_normal;
+    double gamma_draw;
+    } cavb200_bussi_args;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+int cavb200_version(void);
+/* Binds to `device` (cudaSetDevice) and allocates the workspace.  Replaces the GPUArray members
+ * m_temp_energy / m_temp_dipole / m_photon_idx / m_dipole_global of the reference host class
+ * (src/CavityForceComputeGPU.h:50-53, .cc:43-54). */
+int cavb200_create(cavb200_handle** out, int device);
+int cavb200_destroy(cavb200_handle* h);
+const char* cavb200_error_string(int err);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+uint64_t cavb200_launch_count(const cavb200_handle* h);
+/* Tuning knobs ("force_ctas_per_sm", "force_threads", "variant", ...); unknown key -> 1. */
+int cavb200_set_tuning(cavb200_handle* h, const char* key, int value);
+int cavb200_get_tuning(const cavb200_handle* h, const char* key, int* value);
+
+/* ---- cavity force ---------------------------------------------------------------------------
+ * Replaces gpu_compute_cavity_force + the per-step memsets and D2H copies of
+ * CavityForceComputeGPU::computeForces (src/CavityForceComputeGPU.cc:102-253), with the
+ * SEMANTICS of the CPU class CavityForceCompute::computeForces (src/CavityForceCompute.cc:134-208),
+ * which is the parity oracle:
+ *   photon = first index whose type id == L_typeid; none -> all forces and energies zero;
+ *   d = sum_{i != photon} charge_i * (pos_i + image_i * L);   Dq = q_xy + (g/K) d_xy;
+ *   type != L:  force = {(-g*charge)*Dq.x, (-g*charge)*Dq.y, 0, 0};   other 'L': zero;
+ *   photon:     force = {-K q.x - g d.x, -K q.y - g d.y, -K q.z, 0};
+ *   energies {1/2 K q.q, g d_xy.q_xy, 1/2 g^2/K d_xy.d_xy} kept on the device.
+ * Every force[i] (all four components) is overwritten; virial is not touched (the reference never
+ * writes it).  L_typeid = UINT32_MAX means "no type named 'L'" (zero forces, zero energies). */
+int cavb200_force(cavb200_handle* h, const double* pos, const double* charge, const int32_t* image,
+                  double* force, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                  const cavb200_params* params, void* stream);
+
+/* Lazy getters: one small D2H copy + stream sync when called, nothing per step.
+ * Replace getHarmonicEnergy/getCouplingEnergy/getDipoleSelfEnergy (src/CavityForceCompute.cc:58-71). */
+int cavb200_force_read(cavb200_handle* h, double energies[3], double dipole[3], int32_t* photon_idx,
+                       void* stream);
+
+/* ---- Bussi reservoir thermostat ---------------------------------------------------------------
+ * KE = 1/2 sum_group m |v|^2 (HOOMD ComputeThermo, consumed at BussiReservoirThermostat.h:50-55),
+ * alpha = compute_rescale_factor(KE, dof, dt, kT, draws) (:177-225), reservoir bookkeeping
+ * delta = KE (1 - alpha^2), cumulative += delta (:86-95) and v <- alpha v, in ONE launch.
+ * group_idx == NULL means the contiguous group [group_first, group_first + n).
+ * KE == 0 with dof != 0 sets the error flag read back by cavb200_bussi_read (the reference throws
+ * "Bussi thermostat requires non-zero initial momenta", :57-61) and leaves velocities untouched. */
+int cavb200_bussi(cavb200_handle* h, double* vel, const uint32_t* group_idx, uint32_t group_first,
+                  uint32_t n, const cavb200_bussi_args* args, void* stream);
+/* KE reduction only (what getRescalingFactorsOne needs when HOOMD itself applies the rescale). */
+int cavb200_bussi_ke(cavb200_handle* h, const double* vel, const uint32_t* group_idx,
+                     uint32_t group_first, uint32_t n, void* stream);
+/* out = {KE before, alpha, instantaneous reservoir, cumulative reservoir, error flag}. */
+int cavb200_bussi_read(cavb200_handle* h, double out[5], void* stream);
+/* resetReservoirEnergy (src/BussiReservoirThermostat.h:153-159). */
+int cavb200_bussi_reset(cavb200_handle* h, void* stream);
+
+/* ---- fused step: cavity force + Bussi in one launch --------------------------------------------
+ * The north-star "each particle makes one HBM round trip per step": one persistent kernel reduces
+ * the dipole and the kinetic energy together, crosses one grid barrier, then writes forces and
+ * rescaled velocities.  Same results as cavb200_force followed by cavb200_bussi.
+ * The Bussi group is the contiguous range [group_first, group_first + n_group). */
+int cavb200_step(cavb200_handle* h, const double* pos, const double* charge, const int32_t* image,
+                 double* force, double* vel, uint32_t N, double Lx, double Ly, double Lz,
+                 uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
+                 uint32_t n_group, const cavb200_bussi_args* bussi, void* stream);
+
+/* ---- F(k,t): density field --------------------------------------------------------------------
+ * rho[t][k] = sum_j exp(i kvec[k] . r_j(t)) over ALL N particles of frame t (wrapped positions),
+ * the batched form of compute_density_field (reference src/cavitymd/analysis.py:34-47).
+ * pos: T frames of N particles, `stride` doubles per particle (3 = xyz, 4 = HOOMD Scalar4),
+ * frame t starts at pos + t*frame_stride doubles.  kvec: double[3*K] (device).
+ * rho: double[2*K*T] (device), interleaved {re, im}.  Deterministic (fixed-order) reduction. */
+int cavb200_rhok(cavb200_handle* h, const double* pos, uint32_t stride, uint64_t frame_stride,
+                 uint32_t N, uint32_t T, const double* kvec, uint32_t K, double* rho, void* stream);
+/* F[o][l] = mean_k Re(rho[o][k] * conj(rho[o+l][k])) for origins o < n_origins, lags l < n_lags
+ * with o + l < T (compute_field_autocorr, analysis.py:359-364).  out: double[n_origins*n_lags],
+ * entries with o + l >= T are set to NaN. */
+int cavb200_fkt(cavb200_handle* h, const double* rho, uint32_t T, uint32_t K, uint32_t n_origins,
+                uint32_t n_lags, double* out, void* stream);
+
+/* ---- particle-sharded multi-GPU (one process per GPU) -------------------------------------------
+ * New functionality (the reference never reduces across ranks): each rank holds a
+ * contiguous block of particles; between the reduce pass and the apply pass the ranks combine
+ * {d (compensated pairs), first-photon index and position, KE} in rank-ascending order.
+ *   mode 0: ncclAllGather of the 128-byte per-rank record (libnccl resolved with dlopen)
+ *   mode 1: one-shot NVLink exchange -- the reduce kernel's last block stores the record into
+ *           every peer's mailbox (CUDA IPC peer memory) and the apply kernel spins on its own. */
+#define CAVB200_SHARD_RECORD_BYTES 128
+#define CAVB200_NCCL_UNIQUE_ID_BYTES 128
+int cavb200_shard_nccl_unique_id(void* out128);
+int cavb200_shard_init_nccl(cavb200_handle* h, const void* unique_id128, int rank, int nranks);
+/* IPC mailbox: every rank exports its mailbox handle (64 bytes), gathers all ranks' handles by
+ * any host-side means (bench.py uses torch.distributed) and opens them. */
+int cavb200_shard_mailbox_export(cavb200_handle* h, void* out64);
+int cavb200_shard_mailbox_open(cavb200_handle* h, const void* handles64_x_nranks, int rank, int nranks);
+int cavb200_shard_set_mode(cavb200_handle* h, int mode);
+/* `index_offset` = global index of this rank's first particle (photon index is global). */
+int cavb200_shard_step(cavb200_handle* h, const double* pos, const double* charge, const int32_t* image,
+                       double* force, double* vel, uint32_t N_local, uint64_t index_offset,
+                       double Lx, double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params,
+                       uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi,
+                       void* stream);
+
+/* ---- host-buffer entry points (end-to-end path) ------------------------------------------------
+ * Same results as cavb200_step but every array is a HOST pointer: inputs are staged host->device
+ * in chunks that overlap the reduce pass, results are copied back while later chunks compute.
+ * This is what bench.py's "e2e" measures.  Pinned host memory (cavb200_host_alloc) gives full
+ * PCIe speed; pageable memory works but is slower.  Synchronous: returns when outputs are on the
+ * host.  energies[3] and bussi_out[5] may be NULL. */
+int cavb200_step_host(cavb200_handle* h, const double* pos, const double* charge, const int32_t* image,
+                      double* force, double* vel, uint32_t N, double Lx, double Ly, double Lz,
+                      uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
+                      uint32_t n_group, const cavb200_bussi_args* bussi, double energies[3],
+                      double bussi_out[5]);
+
+/* ---- device/host memory helpers for harnesses that have no CUDA runtime of their own ------------
+ * (tests/, bench.py and the ctypes host mirror use these; a HOOMD build never needs them). */
+int cavb200_device_count(int* n);
+int cavb200_dev_alloc(void** ptr, uint64_t bytes);
+int cavb200_dev_free(void* ptr);
+int cavb200_host_alloc(void** ptr, uint64_t bytes); /* pinned */
+int cavb200_host_free(void* ptr);
+int cavb200_memcpy_h2d(void* dst, const void* src, uint64_t bytes, void* stream);
+int cavb200_memcpy_d2h(void* dst, const void* src, uint64_t bytes, void* stream);
+int cavb200_memcpy_d2d(void* dst, const void* src, uint64_t bytes, void* stream);
+int cavb200_memset(void* dst, int value, uint64_t bytes, void* stream);
+int cavb200_stream_create(void** stream);
+int cavb200_stream_destroy(void* stream);
+int cavb200_stream_sync(void* stream);
+int cavb200_device_sync(void);
+/* CUDA-event timing on the launching stream (bench.py): */
+int cavb200_event_create(void** ev);
+int cavb200_event_destroy(void* ev);
+int cavb200_event_record(void* ev, void* stream);
+int cavb200_event_elapsed_ms(void* start, void* stop, float* ms); /* syncs on `stop` */
+/* CUDA-graph capture of a fixed sequence of calls on `stream` (launch-bound inner loops): */
+int cavb200_graph_begin(void* stream);
+int cavb200_graph_end(void* stream, void** graph_exec);
+int cavb200_graph_launch(void* graph_exec, void* stream);
+int cavb200_graph_destroy(void* graph_exec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAVB200_H */
