@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcavb200.so")
+LIB_PATH = os.environ.get("CAVB200_LIB") or os.path.join(_HERE, "lib", "libcavb200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cavb200.h")
 
 
@@ -55,6 +55,7 @@ _SIGNATURES = {
     "cavb200_destroy": (C.c_int, [_vp]),
     "cavb200_error_string": (C.c_char_p, [C.c_int]),
     "cavb200_launch_count": (_u64, [_vp]),
+    "cavb200_debug_stamps": (C.c_int, [_vp, C.POINTER(C.c_uint64), _u32]),
     "cavb200_set_tuning": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "cavb200_get_tuning": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int)]),
     "cavb200_force": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _vp]),
@@ -294,6 +295,12 @@ class Handle:
         v = C.c_int(0)
         check(self.lib.cavb200_get_tuning(self.h, key.encode(), C.byref(v)), f"cavb200_get_tuning({key})")
         return v.value
+
+    def debug_stamps(self, n_ctas: int) -> np.ndarray:
+        out = np.zeros((n_ctas, 8), dtype=np.uint64)
+        check(self.lib.cavb200_debug_stamps(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64)), n_ctas),
+              "cavb200_debug_stamps")
+        return out
 
     @property
     def launch_count(self) -> int:

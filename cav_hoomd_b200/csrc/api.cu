@@ -9,6 +9,35 @@
 
 using namespace cavb;
 
+namespace cavb
+    {
+// The constants the reference forms once per call on the host (CavityForceCompute.cc:174-183), in its
+// operation order; IEEE double on both sides, so the device sees bit-identical values.
+void fill_force_constants(ForceIn& f)
+    {
+    f.gk = f.g / f.K;
+    f.half_K = 0.5 * f.K;
+    f.half_g2K = 0.5 * (f.g * f.g / f.K);
+    }
+
+// BussiReservoirThermostat.h:186-214: everything that does not depend on the kinetic energy.
+void fill_bussi_constants(BussiIn& b, const cavb200_bussi_args* a)
+    {
+    b.kT = a->kT;
+    b.dof = a->dof;
+    b.r_normal = a->r_normal;
+    b.c = (a->tau != 0.0) ? exp(-a->deltaT / a->tau) : 0.0; // :186-190, host libm like the reference
+    b.r_gamma = (a->dof > 1.0) ? 2.0 * a->gamma_draw : 0.0; // :195-200
+    b.half_kT = a->kT / 2.0;                                // :202  set_T / 2.0 / K
+    b.omc = 1.0 - b.c;
+    b.gR2 = b.r_gamma + b.r_normal * b.r_normal;            // :203
+    b.two_R = 2.0 * b.r_normal;                             // :204
+    b.cdof = b.c * a->dof;                                  // :213  c * dof * K / ((1 - c) * K_bar)
+    const double K_bar = a->kT * a->dof / 2.0;              // :212
+    b.den = (1.0 - b.c) * K_bar;
+    }
+    } // namespace cavb
+
 namespace
     {
 inline bool misaligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
@@ -32,6 +61,7 @@ int fill_force(ForceIn& f, const double* pos, const double* charge, const int32_
     f.L_typeid = L_typeid;
     f.g = p->couplstr;
     f.K = p->K;
+    fill_force_constants(f);
     return 0;
     }
 
@@ -48,16 +78,9 @@ int fill_bussi(BussiIn& b, double* vel, const uint32_t* gidx, uint32_t first, ui
     b.n = n;
     b.rescale = rescale;
     b.kT = b.c = b.dof = b.r_normal = b.r_gamma = 0.0;
+    b.half_kT = b.omc = b.gR2 = b.two_R = b.cdof = b.den = 0.0;
     if (a)
-        {
-        b.kT = a->kT;
-        b.dof = a->dof;
-        b.r_normal = a->r_normal;
-        // BussiReservoirThermostat.h:186-190 -- evaluated with the host libm like the reference
-        b.c = (a->tau != 0.0) ? exp(-a->deltaT / a->tau) : 0.0;
-        // :195-200
-        b.r_gamma = (a->dof > 1.0) ? 2.0 * a->gamma_draw : 0.0;
-        }
+        fill_bussi_constants(b, a);
     return 0;
     }
     } // namespace
@@ -98,6 +121,7 @@ int cavb200_create(cavb200_handle** out, int device)
     if ((e = cudaMalloc((void**)&h->partials, sizeof(Partial) * MAX_PARTIALS)) != cudaSuccess
         || (e = cudaMalloc((void**)&h->scalars, sizeof(Scalars))) != cudaSuccess
         || (e = cudaMalloc((void**)&h->counters, 1024)) != cudaSuccess
+        || (e = cudaMalloc((void**)&h->stamps, 8 * sizeof(unsigned long long) * MAX_PARTIALS)) != cudaSuccess
         || (e = cudaMemset(h->scalars, 0, sizeof(Scalars))) != cudaSuccess
         || (e = cudaMemset(h->counters, 0, 1024)) != cudaSuccess
         || (e = cudaMemset(h->partials, 0, sizeof(Partial) * MAX_PARTIALS)) != cudaSuccess)
@@ -106,10 +130,11 @@ int cavb200_create(cavb200_handle** out, int device)
         return (int)e;
         }
     h->tune.variant = 1;
-    h->tune.threads = 512;
+    h->tune.threads = 384;
     h->tune.ctas_per_sm = 2;
     h->tune.unroll = 2;
     h->tune.prefetch = 0;
+    h->tune.pdl = 1;
     h->tune.rhok_threads = 256;
     h->tune.rhok_kblock = 8;
     h->shard.mode = 0;
@@ -128,12 +153,21 @@ int cavb200_destroy(cavb200_handle* h)
     cudaFree(h->partials);
     cudaFree(h->scalars);
     cudaFree(h->counters);
+    cudaFree(h->stamps);
     cudaFree(h->rhok_partials);
     free(h);
     return 0;
     }
 
 uint64_t cavb200_launch_count(const cavb200_handle* h) { return h ? h->launches : 0; }
+
+int cavb200_debug_stamps(cavb200_handle* h, uint64_t* out, uint32_t n_ctas)
+    {
+    if (!h || !out || n_ctas > (uint32_t)MAX_PARTIALS)
+        return (int)cudaErrorInvalidValue;
+    CAVB_CHECK(cudaMemcpy(out, h->stamps, 8ull * sizeof(unsigned long long) * n_ctas, cudaMemcpyDeviceToHost));
+    return 0;
+    }
 
 static int* tuning_slot(cavb::Tuning* t, const char* key)
     {
@@ -142,6 +176,8 @@ static int* tuning_slot(cavb::Tuning* t, const char* key)
     if (!strcmp(key, "ctas_per_sm")) return &t->ctas_per_sm;
     if (!strcmp(key, "unroll")) return &t->unroll;
     if (!strcmp(key, "prefetch")) return &t->prefetch;
+    if (!strcmp(key, "stamps")) return &t->stamps;
+    if (!strcmp(key, "pdl")) return &t->pdl;
     if (!strcmp(key, "rhok_threads")) return &t->rhok_threads;
     if (!strcmp(key, "rhok_kblock")) return &t->rhok_kblock;
     return nullptr;
@@ -158,7 +194,7 @@ int cavb200_set_tuning(cavb200_handle* h, const char* key, int value)
         return (int)cudaErrorInvalidValue;
     if (!strcmp(key, "ctas_per_sm") && (value < 1 || value > 32))
         return (int)cudaErrorInvalidValue;
-    if (!strcmp(key, "unroll") && value != 1 && value != 2 && value != 4)
+    if (!strcmp(key, "unroll") && value != 2 && value != 4 && value != 8)
         return (int)cudaErrorInvalidValue;
     *slot = value;
     return 0;

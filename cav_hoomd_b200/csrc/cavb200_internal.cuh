@@ -18,22 +18,35 @@
 namespace cavb
     {
 constexpr uint32_t NO_INDEX = 0xFFFFFFFFu;
+constexpr unsigned long long HANDOFF_TIMEOUT_NS = 50000000ull; // 50 ms: a co-resident grid hands off in microseconds
 constexpr int MAX_PARTIALS = 2048; // upper bound on the grid of a reduce pass
 
-// One reduce-pass record per CTA (and, in sharded mode, per rank): 128 bytes.
+// One reduce-pass record per CTA (and, in sharded mode, per rank): 160 bytes = five 32-byte sectors,
+// each written with ONE STG.256 and read with ONE LDG.256.  Every sector carries three payload words
+// and a check word  w = epoch ^ payload0 ^ payload1 ^ payload2  (bitwise), so a reader can tell a
+// complete sector of THIS launch from a stale or torn one without any fence or flag: the hand-off
+// between the reduce and apply halves of the cooperative kernel is "store the sectors / poll the
+// sectors".  It relies only on 8-byte access atomicity; a torn or stale sector passes the check
+// with probability 2^-64.  The common path of the combine reads sectors 0-2 (2 only for the
+// thermostat); 3 is read by the one thread whose record holds the photon, 4 only when more than
+// one particle of type 'L' exists.
 // d is carried as unevaluated (hi, lo) pairs so that combining is (nearly) exact and therefore
 // independent of how many CTAs / ranks took part up to the final rounding.
-struct __align__(16) Partial
+constexpr unsigned long long MULTI_L_BIT = 1ull << 63; // in first_L: "this record saw more than one 'L'"
+struct __align__(32) Partial
     {
     double dhi[3];
+    unsigned long long w0;
     double dlo[3];
-    double ke;           // sum m |v|^2 (NOT halved)
-    double q[3];         // unwrapped position of this CTA's first 'L' particle
-    double t[3];         // its dipole term charge*u (added back if it is not the global first)
-    double pad_d;
-    unsigned long long first_L; // GLOBAL index of that particle, ~0ull if none
-    unsigned int n_L;    // number of 'L' particles seen
-    unsigned int pad;
+    unsigned long long w1;
+    double ke;                  // sum m |v|^2 (NOT halved)
+    unsigned long long first_L; // GLOBAL index of the first 'L' particle seen (| MULTI_L_BIT), ~0ull if none
+    unsigned long long n_L;     // number of 'L' particles seen (0, 1, or "2 = more than one" after a merge)
+    unsigned long long w2;
+    double q[3];                // unwrapped position of that first 'L' particle
+    unsigned long long w3;
+    double t[3];                // its dipole term charge*u (goes back into d if it is not the global first)
+    unsigned long long w4;
     };
 static_assert(sizeof(Partial) == CAVB200_SHARD_RECORD_BYTES, "record size is part of the ABI");
 
@@ -65,6 +78,8 @@ struct Tuning
     int ctas_per_sm;     // resident CTAs per SM the grid is sized for
     int unroll;          // independent particle loads in flight per thread (1, 2 or 4)
     int prefetch;        // cooperative variant: issue the apply pass's first loads before the barrier
+    int pdl;             // launch with programmatic stream serialization (hides the launch gap)
+    int stamps;          // debug: record per-CTA phase timestamps of the cooperative kernel
     int rhok_threads;
     int rhok_kblock;     // k-vectors handled per thread in the F(k,t) kernel
     };
@@ -90,8 +105,9 @@ struct cavb200_handle
     int coop_supported;
     cavb::Partial* partials;          // MAX_PARTIALS records
     cavb::Scalars* scalars;           // 1 record
-    unsigned long long* counters;     // [0] barrier arrivals, [1] departures, [4] reduce-pass ticket, [8..] Final
+    unsigned long long* counters;     // [2] hand-off epoch, [4] reduce-pass ticket, [8..] Final (variant 0)
     uint64_t launches;
+    unsigned long long* stamps;       // MAX_PARTIALS x 8 timestamps (debug)
     cavb::Tuning tune;
     cavb::ShardState shard;
     // host-buffer pipeline staging (grown on demand, owned)
@@ -111,9 +127,28 @@ namespace cavb
 __device__ __forceinline__ double4 ld256_stream(const double4* p)
     {
     double4 r;
+    // read once per step: do not keep it in L1, and mark it first to leave L2 (the 126 MB L2 is wanted
+    // for the charge / velocity lines the apply pass reads again and for the dirty output lines)
+#ifndef CAVB_NO_L2_HINTS
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+#endif
                  : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
                  : "l"(p));
+    return r;
+    }
+// streaming read of data that this kernel later overwrites (velocities): no L1 allocation, but not
+// .nc (the non-coherent path requires the data to be read-only for the whole kernel)
+__device__ __forceinline__ double4 ld256_na(const double4* p)
+    {
+    double4 r;
+    // (an L2::evict_last hint here was measured and dropped: with several systems in flight the
+    // pinned-but-dead velocity lines of earlier calls crowd L2; Bussi went from 17.8 to 19.5 us)
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+                 : "l"(p)
+                 : "memory");
     return r;
     }
 __device__ __forceinline__ double4 ld256(const double4* p)
@@ -125,23 +160,49 @@ __device__ __forceinline__ double4 ld256(const double4* p)
                  : "memory");
     return r;
     }
+__device__ __forceinline__ double4 ld256_cg(const double4* p)
+    {
+    double4 r;
+    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+    }
 __device__ __forceinline__ void st256(double4* p, const double4& v)
     {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w)
                  : "memory");
     }
+// output nobody in this library reads again (the force array)
 __device__ __forceinline__ void st256_stream(double4* p, const double4& v)
     {
-    asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y),
-                 "d"(v.z), "d"(v.w)
+#ifndef CAVB_NO_L2_HINTS
+    asm volatile("st.global.L2::evict_first.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w)
                  : "memory");
+#else
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+#endif
     }
+// programmatic dependent launch: wait for the previous kernel of the stream / let the next one start
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
     {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+    }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+    {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+    }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
+    {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
     }
 __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v)
     {
@@ -153,6 +214,12 @@ __device__ __forceinline__ unsigned long long atom_acq_rel_add_u64(unsigned long
     asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
     return old;
     }
+// acq_rel fence at gpu scope (MEMBAR.ALL.GPU): cheaper than __threadfence()'s sequentially
+// consistent MEMBAR.SC.GPU and all the record/flag protocol needs
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// NOTE (measured, round 1): polling with a weak ld.global.cg does NOT work on sm_100 -- a thread
+// whose first poll missed kept reading the stale value until the 2 s guard fired.  Polls and record
+// reads therefore use strong (relaxed, gpu-scope) loads.
 __device__ __forceinline__ unsigned long long globaltimer_ns()
     {
     unsigned long long t;
@@ -196,6 +263,10 @@ struct ForceIn
     double Lx, Ly, Lz;
     uint32_t L_typeid;
     double g, K;
+    // host-evaluated constants, same operation order as the reference (CavityForceCompute.cc:174-183)
+    double gk;       // g / K
+    double half_K;   // 0.5 * K
+    double half_g2K; // 0.5 * (g*g / K)
     };
 struct BussiIn
     {
@@ -203,9 +274,19 @@ struct BussiIn
     const uint32_t* gidx;
     uint32_t first, n;
     double kT, c /* exp(-dt/tau), host-evaluated */, dof, r_normal, r_gamma /* already doubled */;
+    // host-evaluated pieces of compute_rescale_factor that do not depend on KE
+    // (BussiReservoirThermostat.h:202-214, same operation order)
+    double half_kT;  // kT / 2.0
+    double omc;      // 1.0 - c
+    double gR2;      // r_gamma + R*R
+    double two_R;    // 2.0 * R
+    double cdof;     // c * dof
+    double den;      // (1.0 - c) * (kT * dof / 2.0)
     int rescale;         // 0: KE only
     };
 
+void fill_force_constants(ForceIn& f);
+void fill_bussi_constants(BussiIn& b, const cavb200_bussi_args* a);
 int launch_hotpath(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cudaStream_t s);
 int launch_shard_step(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cudaStream_t s);
     } // namespace cavb

@@ -9,16 +9,19 @@ namespace cavb
 // ------------------------------------------------------------------------------------------
 // variant 0, kernel 1: reduce; the last CTA to take a ticket combines and publishes Scalars + Final
 template<bool FORCE, bool BUSSI, int UNROLL, int LB>
-__global__ void __launch_bounds__(LB, 1)
+__global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_reduce(ForceIn f, BussiIn b, Partial* recs, Scalars* scalars, Final* fin_out, unsigned long long* ticket)
     {
     __shared__ BlockScratch sc;
     __shared__ int s_last;
+    pdl_wait();
+    if (threadIdx.x == 0)
+        sc.flags = 0u;
     reduce_phase<FORCE, BUSSI, UNROLL>(f, b, sc);
-    store_record(recs + blockIdx.x, sc.rec);
-    __syncthreads();
+    pdl_launch_dependents();
     if (threadIdx.x == 0)
         {
+        publish_record(recs + blockIdx.x, sc.rec, 0ull);
         __threadfence();
         const unsigned long long t = atom_acq_rel_add_u64(ticket, 1ull);
         s_last = (t == (unsigned long long)gridDim.x - 1);
@@ -26,7 +29,7 @@ __global__ void __launch_bounds__(LB, 1)
     __syncthreads();
     if (!s_last)
         return;
-    combine_phase<FORCE, BUSSI>(recs, (int)gridDim.x, f, b, sc, scalars, true, 0);
+    combine_phase<FORCE, BUSSI, false, true>(recs, (int)gridDim.x, 0ull, f, b, sc, scalars, true);
     if (threadIdx.x == 0)
         {
         *fin_out = sc.fin;
@@ -36,53 +39,58 @@ __global__ void __launch_bounds__(LB, 1)
 
 // variant 0, kernel 2
 template<bool FORCE, bool BUSSI, int UNROLL, int LB>
-__global__ void __launch_bounds__(LB, 1) k_apply(ForceIn f, BussiIn b, const Final* fin_in)
+__global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1) k_apply(ForceIn f, BussiIn b, const Final* fin_in)
     {
     __shared__ Final fin;
+    pdl_wait();
+    pdl_launch_dependents();
     if (threadIdx.x == 0)
         fin = *fin_in;
     __syncthreads();
     apply_phase<FORCE, BUSSI, UNROLL>(fin, f, b);
     }
 
-// variant 1: cooperative persistent kernel (co-residency guaranteed by cudaLaunchCooperativeKernel)
+// variant 1: cooperative persistent kernel (co-residency guaranteed by cudaLaunchCooperativeKernel).
+// Hand-off between reduce and apply: the launch's epoch is (last epoch + 1), read from device memory
+// by every CTA before it publishes anything and written back by CTA 0 after its combine -- i.e. after
+// every CTA has published, hence after every CTA has read it.  No host-side state, so the kernel is
+// safe under CUDA-graph replay and for any sequence of grid sizes.
 template<bool FORCE, bool BUSSI, int UNROLL, int LB>
-__global__ void __launch_bounds__(LB, 1)
-    k_fused(ForceIn f, BussiIn b, Partial* recs, Scalars* scalars, unsigned long long* arrivals)
+__global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
+    k_fused(ForceIn f, BussiIn b, Partial* recs, Scalars* scalars, unsigned long long* epoch_ctr,
+            unsigned long long* stamps)
     {
     __shared__ BlockScratch sc;
-    __shared__ int s_timeout;
-    reduce_phase<FORCE, BUSSI, UNROLL>(f, b, sc);
-    store_record(recs + blockIdx.x, sc.rec);
-    __syncthreads();
+    // optional phase stamps (tools/phase_stamps.py): thread 0 of every CTA, globaltimer ns
+    unsigned long long* my_stamps = (stamps && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
+    if (my_stamps)
+        my_stamps[0] = globaltimer_ns();
+    // programmatic dependent launch: this grid may have been scheduled while the previous kernel of
+    // the stream was still draining; nothing below may touch global memory before this returns
+    pdl_wait();
     if (threadIdx.x == 0)
         {
-        __threadfence();
-        // arrive / spin / depart.  The last CTA to depart zeroes both counters, so the next launch on
-        // this handle (stream-ordered, any grid size, also under CUDA-graph replay) starts clean.
-        atom_acq_rel_add_u64(arrivals, 1ull);
-        int timeout = 0;
-        const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_u64(arrivals) < (unsigned long long)gridDim.x)
-            {
-            if (globaltimer_ns() - t0 > 2000000000ull) // 2 s: never hang the GPU
-                {
-                timeout = 1;
-                break;
-                }
-            }
-        if (atom_acq_rel_add_u64(arrivals + 1, 1ull) == (unsigned long long)gridDim.x - 1ull)
-            {
-            arrivals[0] = 0ull;
-            arrivals[1] = 0ull;
-            }
-        s_timeout = timeout;
+        sc.flags = 0u;
+        sc.epoch = ld_relaxed_u64(epoch_ctr) + 1ull;
         }
-    __syncthreads();
-    combine_phase<FORCE, BUSSI>(recs, (int)gridDim.x, f, b, sc, scalars, blockIdx.x == 0, s_timeout);
-    if (s_timeout)
+    reduce_phase<FORCE, BUSSI, UNROLL>(f, b, sc); // (its barriers also publish sc.epoch to the block)
+    if (threadIdx.x == 0)
+        publish_record(recs + blockIdx.x, sc.rec, sc.epoch);
+    if (my_stamps)
+        my_stamps[1] = globaltimer_ns();
+    const unsigned long long epoch = sc.epoch;
+    combine_phase<FORCE, BUSSI, true, true>(recs, (int)gridDim.x, epoch, f, b, sc, scalars, blockIdx.x == 0, my_stamps);
+    if (my_stamps)
+        my_stamps[3] = globaltimer_ns();
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        *epoch_ctr = epoch;
+    if (sc.fin.timeout)
         return;
+    // from here on the next kernel's CTAs may take the SMs this grid's CTAs leave
+    pdl_launch_dependents();
     apply_phase<FORCE, BUSSI, UNROLL>(sc.fin, f, b);
+    if (my_stamps)
+        my_stamps[4] = globaltimer_ns();
     }
 
 // ------------------------------------------------------------------------------------------
@@ -117,37 +125,93 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         const int grid = (int)(want < (unsigned long long)max_grid ? want : (unsigned long long)max_grid);
         Partial* recs = h->partials;
         Scalars* sca = h->scalars;
-        unsigned long long* arr = h->counters;
+        unsigned long long* arr = h->counters + 2;
         ForceIn ff = f;
         BussiIn bb = b;
-        void* args[] = {&ff, &bb, &recs, &sca, &arr};
-        CAVB_CHECK(cudaLaunchCooperativeKernel((const void*)k_fused<FORCE, BUSSI, UNROLL, LB>, dim3(grid), dim3(threads),
-                                               args, 0, s));
+        unsigned long long* stamps = h->tune.stamps ? h->stamps : nullptr;
+        void* args[] = {&ff, &bb, &recs, &sca, &arr, &stamps};
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attrs[2];
+        int na = 0;
+        if (h->tune.pdl)
+            {
+            // PDL and the cooperative attribute are mutually exclusive; the grid is sized from the
+            // occupancy query above, so all CTAs are co-resident on an otherwise idle device, and the
+            // hand-off spin is bounded (HANDOFF_TIMEOUT_NS) if they ever are not
+            attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attrs[na].val.programmaticStreamSerializationAllowed = 1;
+            na++;
+            }
+        else
+            {
+            attrs[na].id = cudaLaunchAttributeCooperative;
+            attrs[na].val.cooperative = 1;
+            na++;
+            }
+        cfg.attrs = attrs;
+        cfg.numAttrs = na;
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_fused<FORCE, BUSSI, UNROLL, LB>, args));
         h->launches += 1;
         return 0;
         }
 
     const int grid = (int)(want < (unsigned long long)max_grid ? want : (unsigned long long)max_grid);
-    k_reduce<FORCE, BUSSI, UNROLL, LB><<<grid, threads, 0, s>>>(f, b, h->partials, h->scalars, fin_dev, h->counters + 4);
-    CAVB_CHECK(cudaGetLastError());
-    k_apply<FORCE, BUSSI, UNROLL, LB><<<grid, threads, 0, s>>>(f, b, fin_dev);
-    CAVB_CHECK(cudaGetLastError());
+        {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(threads);
+        cfg.stream = s;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = h->tune.pdl ? 1 : 0;
+        ForceIn ff = f;
+        BussiIn bb = b;
+        Partial* recs = h->partials;
+        Scalars* sca = h->scalars;
+        unsigned long long* ticket = h->counters + 4;
+        void* a1[] = {&ff, &bb, &recs, &sca, &fin_dev, &ticket};
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_reduce<FORCE, BUSSI, UNROLL, LB>, a1));
+        const Final* fin_c = fin_dev;
+        void* a2[] = {&ff, &bb, &fin_c};
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_apply<FORCE, BUSSI, UNROLL, LB>, a2));
+        }
     h->launches += 2;
     return 0;
     }
 
+// Launch shapes: the unroll factor fixes the register budget (launch bound).  More loads in flight
+// per thread (ILP) with FEWER threads keeps the same bytes in flight per SM while shrinking the
+// block-wide trees, which are FP64-throughput bound when 32 warps per SM run them:
+//   unroll 2 -> up to  384 threads/CTA,  80 registers (two CTAs per SM)  [default]
+//               up to 1024 threads/CTA,  64 registers
+//   unroll 4 -> up to  512 threads/CTA, 128 registers (one CTA per SM)
+//   unroll 8 -> up to  256 threads/CTA, 255 registers (one CTA per SM)
 template<bool FORCE, bool BUSSI>
 static int launch_u(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaStream_t s)
     {
-    const bool wide = h->tune.threads <= 512 && h->tune.ctas_per_sm == 1;
     switch (h->tune.unroll)
         {
-    case 1:
-        return wide ? launch_t<FORCE, BUSSI, 1, 512>(h, f, b, s) : launch_t<FORCE, BUSSI, 1, 1024>(h, f, b, s);
+    case 8:
+        if (h->tune.threads > 256)
+            return (int)cudaErrorInvalidConfiguration;
+        return launch_t<FORCE, BUSSI, 8, 256>(h, f, b, s);
     case 4:
-        return wide ? launch_t<FORCE, BUSSI, 4, 512>(h, f, b, s) : launch_t<FORCE, BUSSI, 4, 1024>(h, f, b, s);
+        if (h->tune.threads > 512)
+            return (int)cudaErrorInvalidConfiguration;
+        return launch_t<FORCE, BUSSI, 4, 512>(h, f, b, s);
     default:
-        return wide ? launch_t<FORCE, BUSSI, 2, 512>(h, f, b, s) : launch_t<FORCE, BUSSI, 2, 1024>(h, f, b, s);
+        // two 384-thread CTAs per SM (24 warps, 80 registers): the shape that keeps the fused
+        // force + KE loop out of local memory (profiles/microprod_r1b.txt); wider CTAs fall back
+        // to the 64-register build
+        if (h->tune.threads <= 384)
+            return launch_t<FORCE, BUSSI, 2, 384>(h, f, b, s);
+        return launch_t<FORCE, BUSSI, 2, 1024>(h, f, b, s);
         }
     }
 

@@ -1,17 +1,26 @@
-// hotpath.cuh -- device functions of the streaming kernels of the cavity force and the Bussi thermostat (sm_100a).
+// hotpath.cuh -- device functions of the streaming kernels of the cavity force and the Bussi
+// thermostat (sm_100a).
 //
 // Every call is "reduce, combine, apply":
 //   reduce   stream pos/charge/image (52 B/particle) and/or vel (32 B) once, accumulating the dipole
 //            d = sum c_i (r_i + n_i L) as compensated (hi, lo) pairs, sum m|v|^2, and the first
 //            particle of type 'L' (index, unwrapped position, dipole term);
-//   combine  G per-CTA records (128 B each) -> d, KE, photon, Dq, F_L, energies, alpha.  Fixed
-//            order, so results are bitwise reproducible for a given launch shape;
+//   combine  G per-CTA records -> d, KE, photon, Dq, F_L, energies, alpha.  Fixed order, so results
+//            are bitwise reproducible for a given launch shape;
 //   apply    force_i = {(-g c_i) Dq.x, (-g c_i) Dq.y, 0, 0} (8 B read + 32 B write per particle) and
 //            v_i <- alpha v_i (32 B read + 32 B write).
-// Two launch shapes of the same three device functions:
-//   variant 0  reduce kernel (last CTA to finish does the combine) + apply kernel
-//   variant 1  one cooperative persistent kernel: reduce, grid barrier, every CTA combines the
-//              same records in the same order, apply.
+// Launch shapes built from these functions (hotpath.cu, shard.cu):
+//   variant 1  ONE cooperative persistent kernel: reduce, grid-wide hand-off, every CTA combines the
+//              same records in the same order, apply.  The hand-off has no counter and no atomic:
+//              each CTA publishes its record and then an epoch flag inside the record; thread j of
+//              every CTA polls record j's flag and reads the record the moment it is there.
+//   variant 0  reduce kernel (last CTA to take a ticket combines) + apply kernel.
+//
+// Why the combine looks the way it does (profiles/ round-1 notes): with one 128-byte record per CTA
+// read as eight 16-byte requests by all 296 CTAs, the hand-off took 5.5 us -- 700 k requests
+// hammering 296 L2 lines.  Records are therefore laid out in 32-byte sectors read with LDG.256 and
+// the common path touches three sectors.
+//
 // The arithmetic of the per-particle terms, Dq, F_L, the energies and alpha follows the reference
 // operation by operation (src/CavityForceCompute.cc:91-129,169-207 and
 // src/BussiReservoirThermostat.h:177-225): explicit __dmul_rn/__dadd_rn so nothing is contracted
@@ -31,17 +40,22 @@ struct Final
     double FL[3];
     double alpha;
     long long photon_local; // index within this call's arrays, or -1
-    unsigned int n_L;
+    int many_L;             // more than one particle of type 'L' exists
     int has_photon;
     int bussi_ok;
+    int timeout;
     };
 
-struct __align__(16) BlockScratch
+struct __align__(32) BlockScratch
     {
-    double red[32][8];
-    unsigned int red_u[32];
+    double red[8][32]; // [component][warp]: conflict-free when lane == warp index
     unsigned long long red_ull[32];
+    unsigned int red_cnt[32]; // per-warp count of records holding an 'L' candidate (bit 31: multi flag)
+    double wq[32][3];         // per-warp: q of the warp's best candidate
+    double wt[32][3];         // per-warp: its dipole term (kept only by rank-level merges)
     unsigned int min_cand;
+    unsigned int flags; // bit 0: hand-off timed out
+    unsigned long long epoch;
     Partial rec;
     Final fin;
     };
@@ -56,6 +70,79 @@ struct Acc
     unsigned int cand; // first 'L' particle this thread met (local index)
     unsigned int n_L;
     };
+
+__device__ __forceinline__ void acc_zero(Acc& a)
+    {
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        a.dhi[k] = a.dlo[k] = 0.0;
+    a.ke = 0.0;
+    a.cand = NO_INDEX;
+    a.n_L = 0;
+    }
+
+template<bool FORCE, bool BUSSI> __device__ __forceinline__ void warp_tree(Acc& a)
+    {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1)
+        {
+        if (FORCE)
+            {
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                {
+                const double h2 = shfl_xor_d(a.dhi[k], m);
+                const double l2 = shfl_xor_d(a.dlo[k], m);
+                pair_add(a.dhi[k], a.dlo[k], h2, l2);
+                }
+            a.n_L += __shfl_xor_sync(0xffffffffu, a.n_L, m);
+            }
+        if (BUSSI)
+            a.ke += shfl_xor_d(a.ke, m);
+        }
+    }
+
+// Second tree level: lane w of warp 0 picks up warp w's totals from shared memory.
+template<bool FORCE, bool BUSSI>
+__device__ __forceinline__ void cross_warp_put(const Acc& a, BlockScratch& sc, unsigned int lane, unsigned int warp)
+    {
+    if (lane == 0)
+        {
+        if (FORCE)
+            {
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                {
+                sc.red[k][warp] = a.dhi[k];
+                sc.red[3 + k][warp] = a.dlo[k];
+                }
+            sc.red[7][warp] = __longlong_as_double((long long)a.n_L);
+            }
+        if (BUSSI)
+            sc.red[6][warp] = a.ke;
+        }
+    }
+template<bool FORCE, bool BUSSI>
+__device__ __forceinline__ void cross_warp_get(Acc& b, const BlockScratch& sc, unsigned int lane, unsigned int nwarps)
+    {
+    acc_zero(b);
+    if (lane < nwarps)
+        {
+        if (FORCE)
+            {
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                {
+                b.dhi[k] = sc.red[k][lane];
+                b.dlo[k] = sc.red[3 + k][lane];
+                }
+            b.n_L = (unsigned int)__double_as_longlong(sc.red[7][lane]);
+            }
+        if (BUSSI)
+            b.ke = sc.red[6][lane];
+        }
+    warp_tree<FORCE, BUSSI>(b);
+    }
 
 __device__ __forceinline__ void unwrap_term(const double4& p, double c, int ix, int iy, int iz, const ForceIn& f,
                                             double u[3], double t[3])
@@ -86,17 +173,30 @@ __device__ __forceinline__ void take_particle(Acc& a, unsigned int i, const doub
         }
     if (!aside)
         {
+#ifdef CAVB_EXP_PLAIN_SUM
+        a.dhi[0] += t[0];
+        a.dhi[1] += t[1];
+        a.dhi[2] += t[2];
+#else
         two_sum_acc(a.dhi[0], a.dlo[0], t[0]);
         two_sum_acc(a.dhi[1], a.dlo[1], t[1]);
         two_sum_acc(a.dhi[2], a.dlo[2], t[2]);
+#endif
         }
     }
 
 template<int UNROLL> __device__ __forceinline__ void reduce_force(Acc& a, const ForceIn& f)
     {
+#ifdef CAVB_EXP_CHUNK
+    const unsigned long long per = ((f.N + gridDim.x - 1) / gridDim.x + 31) & ~31ull;
+    const unsigned long long stride = blockDim.x;
+    unsigned long long i = per * blockIdx.x + threadIdx.x;
+    const unsigned long long N = min((unsigned long long)f.N, per * (blockIdx.x + 1ull));
+#else
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long N = f.N;
+#endif
     if (UNROLL > 1)
         {
         for (; i + (UNROLL - 1) * stride < N; i += UNROLL * stride)
@@ -110,9 +210,13 @@ template<int UNROLL> __device__ __forceinline__ void reduce_force(Acc& a, const 
                 const unsigned long long j = i + k * stride;
                 p[k] = ld256_stream(f.pos + j);
                 c[k] = __ldg(f.charge + j);
+#ifdef CAVB_EXP_NO_IMAGE
+                ix[k] = iy[k] = iz[k] = 0;
+#else
                 ix[k] = __ldg(f.image + 3 * j + 0);
                 iy[k] = __ldg(f.image + 3 * j + 1);
                 iz[k] = __ldg(f.image + 3 * j + 2);
+#endif
                 }
 #pragma unroll
             for (int k = 0; k < UNROLL; k++)
@@ -132,9 +236,16 @@ template<int UNROLL> __device__ __forceinline__ void reduce_force(Acc& a, const 
 
 template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const BussiIn& b)
     {
+#ifdef CAVB_EXP_CHUNK
+    const unsigned long long per = ((b.n + gridDim.x - 1) / gridDim.x + 31) & ~31ull;
+    const unsigned long long stride = blockDim.x;
+    unsigned long long j = per * blockIdx.x + threadIdx.x;
+    const unsigned long long n = min((unsigned long long)b.n, per * (blockIdx.x + 1ull));
+#else
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long n = b.n;
+#endif
     double ke[UNROLL > 1 ? UNROLL : 1];
 #pragma unroll
     for (int k = 0; k < (UNROLL > 1 ? UNROLL : 1); k++)
@@ -167,108 +278,137 @@ template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const Bus
         a.ke += ke[k];
     }
 
-// Block-wide merge of the per-thread accumulators into `sc.rec` (valid after the call in thread 0,
-// and in shared memory for everyone after the trailing __syncthreads()).
+// ---- fused stream (contiguous Bussi group starting at particle 0) ------------------------------
+// ONE loop reads pos/charge/image AND vel.  Measured with tools/microstream.cu
+// (profiles/microstream_r1b.txt): this access pattern plus this arithmetic streams 84 MB in 13.1 us
+// (6.4 TB/s) at 1024 threads/SM with two particles in flight per thread, but only 4.4 TB/s at 512
+// and 2.1 TB/s at 256 threads/SM -- the per-particle FP64 work needs warps, not unrolling, to hide.
+// Separate force and KE loops (the first version) paid the memory ramp twice.  A software-pipelined
+// variant with predicated loads was slower than this plain "U loads, U consumes" loop and was dropped.
+template<bool FORCE, bool KE, int U>
+__device__ __forceinline__ void reduce_stream(Acc& a, const ForceIn& f, const BussiIn& b)
+    {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long nf = FORCE ? (unsigned long long)f.N : 0ull;
+    const unsigned long long nk = KE ? (unsigned long long)b.n : 0ull; // group = [0, n)
+    const unsigned long long common = (FORCE && KE) ? (nf < nk ? nf : nk) : (FORCE ? nf : nk);
+    const unsigned long long all = nf > nk ? nf : nk;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double ke[U];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+        ke[k] = 0.0;
+    for (; i + (U - 1) * stride < common; i += U * stride)
+        {
+        double4 p[FORCE ? U : 1], v[KE ? U : 1];
+        double c[FORCE ? U : 1];
+        int ix[FORCE ? U : 1], iy[FORCE ? U : 1], iz[FORCE ? U : 1];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            {
+            const unsigned long long j = i + k * stride;
+            if (FORCE)
+                {
+                p[k] = ld256_stream(f.pos + j);
+                c[k] = __ldg(f.charge + j);
+                ix[k] = __ldg(f.image + 3 * j + 0);
+                iy[k] = __ldg(f.image + 3 * j + 1);
+                iz[k] = __ldg(f.image + 3 * j + 2);
+                }
+            if (KE)
+                v[k] = ld256_na(b.vel + j);
+            }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            {
+            if (FORCE)
+                take_particle(a, (unsigned int)(i + k * stride), p[k], c[k], ix[k], iy[k], iz[k], f);
+            if (KE)
+                ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z);
+            }
+        }
+    // tail: fewer than U strides left, and the indices only one of the two ranges covers
+    for (; i < all; i += stride)
+        {
+        if (FORCE && i < nf)
+            {
+            const double4 p = ld256_stream(f.pos + i);
+            const double c = __ldg(f.charge + i);
+            const int ix = __ldg(f.image + 3 * i + 0);
+            const int iy = __ldg(f.image + 3 * i + 1);
+            const int iz = __ldg(f.image + 3 * i + 2);
+            take_particle(a, (unsigned int)i, p, c, ix, iy, iz, f);
+            }
+        if (KE && i < nk)
+            {
+            const double4 v = ld256_na(b.vel + i);
+            ke[0] += v.w * (v.x * v.x + v.y * v.y + v.z * v.z);
+            }
+        }
+    if (KE)
+        {
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            a.ke += ke[k];
+        }
+    }
+
+// Block-wide merge of the per-thread accumulators into sc.rec (shared; complete after the
+// trailing __syncthreads()).
 template<bool FORCE, bool BUSSI>
 __device__ __forceinline__ void block_merge(Acc& a, const ForceIn& f, BlockScratch& sc)
     {
     const unsigned int tid = threadIdx.x;
     const unsigned int lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
 
+    if (tid == 0)
+        {
+        sc.min_cand = NO_INDEX;
+        sc.rec.first_L = ~0ull;
+        sc.rec.q[0] = sc.rec.q[1] = sc.rec.q[2] = 0.0;
+        sc.rec.t[0] = sc.rec.t[1] = sc.rec.t[2] = 0.0;
+        }
     if (FORCE)
         {
-        if (tid == 0)
+        // the vote is only needed when somebody in the block met an 'L' particle
+        const int any = __syncthreads_or(a.cand != NO_INDEX);
+        if (any)
             {
-            sc.min_cand = NO_INDEX;
-            sc.rec.first_L = ~0ull;
-            sc.rec.q[0] = sc.rec.q[1] = sc.rec.q[2] = 0.0;
-            sc.rec.t[0] = sc.rec.t[1] = sc.rec.t[2] = 0.0;
-            }
-        __syncthreads();
-        if (a.cand != NO_INDEX)
-            atomicMin(&sc.min_cand, a.cand);
-        __syncthreads();
-        if (a.cand != NO_INDEX)
-            {
-            // rare path (one thread per system in practice): fetch the particle again
-            const unsigned long long i = a.cand;
-            const double4 p = ld256(f.pos + i);
-            const double c = f.charge[i];
-            double u[3], t[3];
-            unwrap_term(p, c, f.image[3 * i + 0], f.image[3 * i + 1], f.image[3 * i + 2], f, u, t);
-            if (a.cand == sc.min_cand)
+            if (a.cand != NO_INDEX)
+                atomicMin(&sc.min_cand, a.cand);
+            __syncthreads();
+            if (a.cand != NO_INDEX)
                 {
-                sc.rec.first_L = f.index_offset + i;
-                for (int k = 0; k < 3; k++)
+                // rare path (one thread per system in practice): fetch the particle again
+                const unsigned long long i = a.cand;
+                const double4 p = ld256(f.pos + i);
+                const double c = f.charge[i];
+                double u[3], t[3];
+                unwrap_term(p, c, f.image[3 * i + 0], f.image[3 * i + 1], f.image[3 * i + 2], f, u, t);
+                if (a.cand == sc.min_cand)
                     {
-                    sc.rec.q[k] = u[k];
-                    sc.rec.t[k] = t[k];
+                    sc.rec.first_L = f.index_offset + i;
+                    for (int k = 0; k < 3; k++)
+                        {
+                        sc.rec.q[k] = u[k];
+                        sc.rec.t[k] = t[k];
+                        }
+                    }
+                else
+                    {
+                    for (int k = 0; k < 3; k++)
+                        two_sum_acc(a.dhi[k], a.dlo[k], t[k]);
                     }
                 }
-            else
-                {
-                for (int k = 0; k < 3; k++)
-                    two_sum_acc(a.dhi[k], a.dlo[k], t[k]);
-                }
             }
         }
-
-    // warp tree
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1)
-        {
-        if (FORCE)
-            {
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                {
-                const double h2 = shfl_xor_d(a.dhi[k], m);
-                const double l2 = shfl_xor_d(a.dlo[k], m);
-                pair_add(a.dhi[k], a.dlo[k], h2, l2);
-                }
-            a.n_L += __shfl_xor_sync(0xffffffffu, a.n_L, m);
-            }
-        if (BUSSI)
-            a.ke += shfl_xor_d(a.ke, m);
-        }
-    if (lane == 0)
-        {
-        for (int k = 0; k < 3; k++)
-            {
-            sc.red[warp][k] = a.dhi[k];
-            sc.red[warp][3 + k] = a.dlo[k];
-            }
-        sc.red[warp][6] = a.ke;
-        sc.red_u[warp] = a.n_L;
-        }
+    warp_tree<FORCE, BUSSI>(a);
+    cross_warp_put<FORCE, BUSSI>(a, sc, lane, warp);
     __syncthreads();
     if (warp == 0)
         {
         Acc b;
-        for (int k = 0; k < 3; k++)
-            {
-            b.dhi[k] = lane < nwarps ? sc.red[lane][k] : 0.0;
-            b.dlo[k] = lane < nwarps ? sc.red[lane][3 + k] : 0.0;
-            }
-        b.ke = lane < nwarps ? sc.red[lane][6] : 0.0;
-        b.n_L = lane < nwarps ? sc.red_u[lane] : 0u;
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1)
-            {
-            if (FORCE)
-                {
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    {
-                    const double h2 = shfl_xor_d(b.dhi[k], m);
-                    const double l2 = shfl_xor_d(b.dlo[k], m);
-                    pair_add(b.dhi[k], b.dlo[k], h2, l2);
-                    }
-                b.n_L += __shfl_xor_sync(0xffffffffu, b.n_L, m);
-                }
-            if (BUSSI)
-                b.ke += shfl_xor_d(b.ke, m);
-            }
+        cross_warp_get<FORCE, BUSSI>(b, sc, lane, nwarps);
         if (lane == 0)
             {
             for (int k = 0; k < 3; k++)
@@ -278,14 +418,8 @@ __device__ __forceinline__ void block_merge(Acc& a, const ForceIn& f, BlockScrat
                 }
             sc.rec.ke = b.ke;
             sc.rec.n_L = b.n_L;
-            sc.rec.pad = 0;
-            sc.rec.pad_d = 0.0;
-            if (!FORCE)
-                {
-                sc.rec.first_L = ~0ull;
-                sc.rec.q[0] = sc.rec.q[1] = sc.rec.q[2] = 0.0;
-                sc.rec.t[0] = sc.rec.t[1] = sc.rec.t[2] = 0.0;
-                }
+            if (b.n_L > 1 && sc.rec.first_L != ~0ull)
+                sc.rec.first_L |= MULTI_L_BIT;
             }
         }
     __syncthreads();
@@ -295,33 +429,76 @@ template<bool FORCE, bool BUSSI, int UNROLL>
 __device__ __forceinline__ void reduce_phase(const ForceIn& f, const BussiIn& b, BlockScratch& sc)
     {
     Acc a;
-    for (int k = 0; k < 3; k++)
-        a.dhi[k] = a.dlo[k] = 0.0;
-    a.ke = 0.0;
-    a.cand = NO_INDEX;
-    a.n_L = 0;
-    if (FORCE)
-        reduce_force<UNROLL>(a, f);
-    if (BUSSI)
+    acc_zero(a);
+    if (BUSSI && (b.gidx != nullptr || b.first != 0))
+        {
+        // index-list group or a group that does not start at particle 0: the velocity pass cannot
+        // share the particle loop
+        if (FORCE)
+            reduce_stream<true, false, UNROLL>(a, f, b);
         reduce_ke<UNROLL>(a, b);
+        }
+    else
+        reduce_stream<FORCE, BUSSI, UNROLL>(a, f, b);
     block_merge<FORCE, BUSSI>(a, f, sc);
     }
 
-__device__ __forceinline__ void store_record(Partial* dst, const Partial& src)
+// ---- record sectors: payload x3 + check word --------------------------------------------------
+__device__ __forceinline__ unsigned long long dbits(double x) { return (unsigned long long)__double_as_longlong(x); }
+__device__ __forceinline__ double bitsd(unsigned long long x) { return __longlong_as_double((long long)x); }
+__device__ __forceinline__ double4 make_sector(double a, double b, double c, unsigned long long epoch)
     {
-    // 128 B as eight 16-B stores by the first 8 threads
-    const double2* s = reinterpret_cast<const double2*>(&src);
-    double2* d = reinterpret_cast<double2*>(dst);
-    if (threadIdx.x < 8)
-        __stcg(d + threadIdx.x, s[threadIdx.x]);
+    return make_double4(a, b, c, bitsd(epoch ^ dbits(a) ^ dbits(b) ^ dbits(c)));
+    }
+__device__ __forceinline__ bool sector_ok(const double4& s, unsigned long long epoch)
+    {
+    return (dbits(s.x) ^ dbits(s.y) ^ dbits(s.z) ^ dbits(s.w)) == epoch;
+    }
+
+// ONE thread publishes the record: five STG.256, no fence, no flag (see the Partial comment).
+__device__ __forceinline__ void publish_record(Partial* dst, const Partial& src, unsigned long long epoch)
+    {
+    double4* d = reinterpret_cast<double4*>(dst);
+    st256(d + 0, make_sector(src.dhi[0], src.dhi[1], src.dhi[2], epoch));
+    st256(d + 1, make_sector(src.dlo[0], src.dlo[1], src.dlo[2], epoch));
+    st256(d + 2, make_sector(src.ke, bitsd(src.first_L), bitsd(src.n_L), epoch));
+    st256(d + 3, make_sector(src.q[0], src.q[1], src.q[2], epoch));
+    st256(d + 4, make_sector(src.t[0], src.t[1], src.t[2], epoch));
+    }
+
+// Strong (L2) read of one sector; WAIT: poll until it carries this launch's epoch (bounded).
+template<bool WAIT>
+__device__ __forceinline__ double4 read_sector(const double4* p, unsigned long long epoch, bool& late)
+    {
+    double4 s = ld256_cg(p);
+    if (WAIT)
+        {
+        if (!sector_ok(s, epoch))
+            {
+            const unsigned long long t0 = globaltimer_ns();
+            do
+                {
+                __nanosleep(64);
+                s = ld256_cg(p);
+                if (globaltimer_ns() - t0 > HANDOFF_TIMEOUT_NS) // never hang the GPU
+                    {
+                    late = true;
+                    break;
+                    }
+                } while (!sector_ok(s, epoch));
+            }
+        }
+    return s;
     }
 
 // ------------------------------------------------------------------------------------------
-// combine = merge (G records -> one record, block-wide, fixed order) + finalize (thread 0)
+// combine = merge (G records -> one record, fixed order) + finalize
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double bussi_alpha(double KE, const BussiIn& b, int& ok)
     {
-    // BussiReservoirThermostat.h:177-225 with c = exp(-dt/tau) evaluated by the host
+    // BussiReservoirThermostat.h:177-225.  Everything that does not depend on KE was evaluated by
+    // the host in the same operation order (api.cu fill_bussi_constants): c = exp(-dt/tau),
+    // omc = 1 - c, half_kT = kT/2, gR2 = r_gamma + R*R, two_R = 2*R, cdof = c*dof, den = omc*(kT*dof/2).
     ok = 1;
     if (b.dof == 0.0)
         return 1.0;
@@ -330,152 +507,218 @@ __device__ __forceinline__ double bussi_alpha(double KE, const BussiIn& b, int& 
         ok = 0; // the reference throws (:57-61)
         return 1.0;
         }
-    const double c = b.c, R = b.r_normal;
-    const double omc = __dadd_rn(1.0, -c);
-    const double v = __ddiv_rn(__ddiv_rn(b.kT, 2.0), KE);
-    const double vomc = __dmul_rn(v, omc);
-    const double term1 = __dmul_rn(vomc, __dadd_rn(b.r_gamma, __dmul_rn(R, R)));
-    const double term2 = __dmul_rn(__dmul_rn(2.0, R), __dsqrt_rn(__dmul_rn(vomc, c)));
-    const double alpha2 = __dadd_rn(__dadd_rn(c, term1), term2);
+    const double v = __ddiv_rn(b.half_kT, KE);
+    const double vomc = __dmul_rn(v, b.omc);
+    const double term1 = __dmul_rn(vomc, b.gR2);
+    const double term2 = __dmul_rn(b.two_R, __dsqrt_rn(__dmul_rn(vomc, b.c)));
+    const double alpha2 = __dadd_rn(__dadd_rn(b.c, term1), term2);
     const double mag = __dsqrt_rn(alpha2);
-    const double K_bar = __ddiv_rn(__dmul_rn(b.kT, b.dof), 2.0);
-    const double sign_term
-        = __dadd_rn(R, __dsqrt_rn(__ddiv_rn(__dmul_rn(__dmul_rn(c, b.dof), KE), __dmul_rn(omc, K_bar))));
+    const double sign_term = __dadd_rn(b.r_normal, __dsqrt_rn(__ddiv_rn(__dmul_rn(b.cdof, KE), b.den)));
     return sign_term >= 0.0 ? mag : -mag;
     }
 
-// Merge G records (read through L2) into sc.rec.  Every field of sc.rec is valid for ALL threads
-// after the call.  The winner of the first-'L' vote keeps q and t; the losers' terms go back into d
-// (they are ordinary members of the dipole sum, CavityForceCompute.cc:120-126).
 template<bool FORCE, bool BUSSI>
-__device__ __forceinline__ void merge_phase(const Partial* __restrict__ recs, int G, BlockScratch& sc)
+__device__ __forceinline__ void finalize(const ForceIn& f, const BussiIn& b, BlockScratch& sc, Scalars* scalars,
+                                         bool publish);
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
     {
-    const unsigned int tid = threadIdx.x;
-    const unsigned int lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
-
-    // pass 1: global first 'L'
-    unsigned long long gmin = ~0ull;
-    if (FORCE)
-        {
-        for (int r = tid; r < G; r += blockDim.x)
-            {
-            const unsigned long long v = __ldcg(&recs[r].first_L);
-            gmin = v < gmin ? v : gmin;
-            }
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1)
-            {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, gmin, m);
-            gmin = o < gmin ? o : gmin;
-            }
-        __syncthreads(); // sc.rec may still be being read by store_record of the caller
-        if (lane == 0)
-            sc.red_ull[warp] = gmin;
-        if (tid == 0)
-            {
-            sc.rec.q[0] = sc.rec.q[1] = sc.rec.q[2] = 0.0;
-            sc.rec.t[0] = sc.rec.t[1] = sc.rec.t[2] = 0.0;
-            }
-        __syncthreads();
-        gmin = ~0ull;
-        for (unsigned int w = 0; w < nwarps; w++)
-            gmin = sc.red_ull[w] < gmin ? sc.red_ull[w] : gmin;
-        }
-    else
-        __syncthreads();
-
-    // pass 2: pairs in record order
-    Acc a;
-    for (int k = 0; k < 3; k++)
-        a.dhi[k] = a.dlo[k] = 0.0;
-    a.ke = 0.0;
-    a.n_L = 0;
-    for (int r = tid; r < G; r += blockDim.x)
-        {
-        // record layout in 16-byte words: {dhi0,dhi1} {dhi2,dlo0} {dlo1,dlo2} {ke,q0} {q1,q2} {t0,t1}
-        // {t2,pad} {first_L, n_L|pad}
-        const double2* p = reinterpret_cast<const double2*>(recs + r);
-        const double2 v3 = __ldcg(p + 3);
-        if (FORCE)
-            {
-            const double2 v0 = __ldcg(p + 0), v1 = __ldcg(p + 1), v2 = __ldcg(p + 2);
-            pair_add(a.dhi[0], a.dlo[0], v0.x, v1.y);
-            pair_add(a.dhi[1], a.dlo[1], v0.y, v2.x);
-            pair_add(a.dhi[2], a.dlo[2], v1.x, v2.y);
-            const ulonglong2 v7 = __ldcg(reinterpret_cast<const ulonglong2*>(p + 7));
-            a.n_L += (unsigned int)(v7.y & 0xffffffffull);
-            if (v7.x != ~0ull)
-                {
-                const double2 v4 = __ldcg(p + 4), v5 = __ldcg(p + 5), v6 = __ldcg(p + 6);
-                if (v7.x == gmin)
-                    {
-                    sc.rec.q[0] = v3.y;
-                    sc.rec.q[1] = v4.x;
-                    sc.rec.q[2] = v4.y;
-                    sc.rec.t[0] = v5.x;
-                    sc.rec.t[1] = v5.y;
-                    sc.rec.t[2] = v6.x;
-                    }
-                else
-                    {
-                    two_sum_acc(a.dhi[0], a.dlo[0], v5.x);
-                    two_sum_acc(a.dhi[1], a.dlo[1], v5.y);
-                    two_sum_acc(a.dhi[2], a.dlo[2], v6.x);
-                    }
-                }
-            }
-        if (BUSSI)
-            a.ke += v3.x;
-        }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1)
         {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
+        v = o < v ? o : v;
+        }
+    return v;
+    }
+
+// Merge G records into sc.rec and (FINALIZE) form sc.fin / Scalars, all valid for every thread after
+// the call.  Latency is what matters here -- the whole grid is waiting -- so:
+//   * only the warps that hold records work (thread j takes records j, j + blockDim, ...);
+//   * the vote for the first 'L' particle, the pair trees and the finalize need TWO block barriers;
+//   * the photon position (sector 3) is fetched by the one lane whose record holds the candidate,
+//     concurrently with the tree; sector 4 is touched only when several 'L' particles exist.
+template<bool FORCE, bool BUSSI, bool WAIT, bool FINALIZE>
+__device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, int G, unsigned long long epoch,
+                                              const ForceIn& f, const BussiIn& b, BlockScratch& sc, Scalars* scalars,
+                                              bool publish, unsigned long long* dbg = nullptr)
+    {
+    const unsigned int tid = threadIdx.x;
+    const unsigned int lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
+    const unsigned int work_warps = min(nwarps, (unsigned int)((G + 31) >> 5));
+    bool late = false;
+
+    if (warp < work_warps)
+        {
+        Acc a;
+        acc_zero(a);
+        unsigned long long mykey = ~0ull;
+        unsigned int mycnt = 0, mymulti = 0;
+        int myrec = -1;
+        for (int j = tid; j < G; j += blockDim.x)
+            {
+            const double4* p = reinterpret_cast<const double4*>(recs + j);
+            // issue all sector reads before looking at any of them
+            double4 s2 = ld256_cg(p + 2), s0, s1;
+            if (FORCE)
+                {
+                s0 = ld256_cg(p + 0);
+                s1 = ld256_cg(p + 1);
+                }
+            if (WAIT)
+                {
+                if (!sector_ok(s2, epoch))
+                    s2 = read_sector<true>(p + 2, epoch, late);
+                if (FORCE)
+                    {
+                    if (!sector_ok(s0, epoch))
+                        s0 = read_sector<true>(p + 0, epoch, late);
+                    if (!sector_ok(s1, epoch))
+                        s1 = read_sector<true>(p + 1, epoch, late);
+                    }
+                }
+            if (FORCE)
+                {
+                pair_add(a.dhi[0], a.dlo[0], s0.x, s1.x);
+                pair_add(a.dhi[1], a.dlo[1], s0.y, s1.y);
+                pair_add(a.dhi[2], a.dlo[2], s0.z, s1.z);
+                const unsigned long long key = dbits(s2.y);
+                if (key != ~0ull)
+                    {
+                    mycnt++;
+                    mymulti |= (key & MULTI_L_BIT) ? 1u : 0u;
+                    const unsigned long long idx = key & ~MULTI_L_BIT;
+                    if (idx < mykey)
+                        {
+                        mykey = idx;
+                        myrec = j;
+                        }
+                    }
+                }
+            if (BUSSI)
+                a.ke += s2.x;
+            }
+        if (dbg && tid == 0)
+            dbg[2] = globaltimer_ns();
         if (FORCE)
             {
-#pragma unroll
-            for (int k = 0; k < 3; k++)
+            // warp-level vote; the winning lane starts fetching q right away
+            const unsigned long long wmin = warp_min_u64(mykey);
+            const unsigned int wcnt = __reduce_add_sync(0xffffffffu, mycnt);
+            const unsigned int wmulti = __any_sync(0xffffffffu, mymulti != 0);
+            double4 s3 = make_double4(0.0, 0.0, 0.0, 0.0), s4 = s3;
+            const bool i_hold = (wmin != ~0ull) && (mykey == wmin);
+            if (i_hold)
                 {
-                const double h2 = shfl_xor_d(a.dhi[k], m);
-                const double l2 = shfl_xor_d(a.dlo[k], m);
-                pair_add(a.dhi[k], a.dlo[k], h2, l2);
+                s3 = read_sector<WAIT>(reinterpret_cast<const double4*>(recs + myrec) + 3, epoch, late);
+                if (!FINALIZE) // a rank-level merge may lose the global vote later: keep the term too
+                    s4 = read_sector<WAIT>(reinterpret_cast<const double4*>(recs + myrec) + 4, epoch, late);
                 }
-            a.n_L += __shfl_xor_sync(0xffffffffu, a.n_L, m);
+            warp_tree<FORCE, BUSSI>(a);
+            if (i_hold)
+                {
+                sc.wq[warp][0] = s3.x;
+                sc.wq[warp][1] = s3.y;
+                sc.wq[warp][2] = s3.z;
+                sc.wt[warp][0] = s4.x;
+                sc.wt[warp][1] = s4.y;
+                sc.wt[warp][2] = s4.z;
+                }
+            if (lane == 0)
+                {
+                sc.red_ull[warp] = wmin;
+                sc.red_cnt[warp] = wcnt | (wmulti ? 0x80000000u : 0u);
+                }
             }
-        if (BUSSI)
-            a.ke += shfl_xor_d(a.ke, m);
-        }
-    if (lane == 0)
-        {
-        for (int k = 0; k < 3; k++)
-            {
-            sc.red[warp][k] = a.dhi[k];
-            sc.red[warp][3 + k] = a.dlo[k];
-            }
-        sc.red[warp][6] = a.ke;
-        sc.red_u[warp] = a.n_L;
+        else
+            warp_tree<FORCE, BUSSI>(a);
+        cross_warp_put<FORCE, BUSSI>(a, sc, lane, warp);
+        if (late)
+            atomicOr(&sc.flags, 1u);
         }
     __syncthreads();
-    if (tid == 0)
+    if (dbg && tid == 0)
+        dbg[5] = globaltimer_ns();
+    if (warp == 0)
         {
-        double dh[3] = {0, 0, 0}, dl[3] = {0, 0, 0}, kes = 0.0;
-        unsigned int nL = 0;
-        for (unsigned int w = 0; w < nwarps; w++)
+        Acc t;
+        cross_warp_get<FORCE, BUSSI>(t, sc, lane, work_warps);
+        unsigned long long gmin = ~0ull;
+        int many = 0;
+        if (FORCE)
+            {
+            const unsigned long long wkey = lane < work_warps ? sc.red_ull[lane] : ~0ull;
+            const unsigned int wc = lane < work_warps ? sc.red_cnt[lane] : 0u;
+            gmin = warp_min_u64(wkey);
+            const unsigned int cnt = __reduce_add_sync(0xffffffffu, wc & 0x7fffffffu);
+            many = (cnt > 1) || __any_sync(0xffffffffu, (wc & 0x80000000u) != 0);
+            // q of the global winner: the lowest warp whose vote equals gmin
+            const unsigned int holders = __ballot_sync(0xffffffffu, gmin != ~0ull && wkey == gmin);
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0, t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            if (holders)
+                {
+                const int w = __ffs(holders) - 1;
+                q0 = sc.wq[w][0];
+                q1 = sc.wq[w][1];
+                q2 = sc.wq[w][2];
+                t0 = sc.wt[w][0];
+                t1 = sc.wt[w][1];
+                t2 = sc.wt[w][2];
+                }
+            if (many)
+                {
+                // several 'L' particles: every candidate that is not the global first is an ordinary
+                // member of the dipole sum (CavityForceCompute.cc:120-126) -- add its term back
+                Acc extra;
+                acc_zero(extra);
+                bool late2 = false;
+                for (int j = lane; j < G; j += 32)
+                    {
+                    const double4* p = reinterpret_cast<const double4*>(recs + j);
+                    const double4 s2 = read_sector<WAIT>(p + 2, epoch, late2);
+                    const unsigned long long key = dbits(s2.y);
+                    if (key != ~0ull && (key & ~MULTI_L_BIT) != gmin)
+                        {
+                        const double4 s4 = read_sector<WAIT>(p + 4, epoch, late2);
+                        two_sum_acc(extra.dhi[0], extra.dlo[0], s4.x);
+                        two_sum_acc(extra.dhi[1], extra.dlo[1], s4.y);
+                        two_sum_acc(extra.dhi[2], extra.dlo[2], s4.z);
+                        }
+                    }
+                warp_tree<true, false>(extra);
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    pair_add(t.dhi[k], t.dlo[k], extra.dhi[k], extra.dlo[k]);
+                if (late2)
+                    atomicOr(&sc.flags, 1u);
+                }
+            if (lane == 0)
+                {
+                sc.rec.q[0] = q0;
+                sc.rec.q[1] = q1;
+                sc.rec.q[2] = q2;
+                sc.rec.t[0] = t0; // (zero after a final merge: the global first's own term never enters d)
+                sc.rec.t[1] = t1;
+                sc.rec.t[2] = t2;
+                }
+            }
+        if (lane == 0)
             {
             for (int k = 0; k < 3; k++)
-                pair_add(dh[k], dl[k], sc.red[w][k], sc.red[w][3 + k]);
-            kes += sc.red[w][6];
-            nL += sc.red_u[w];
+                {
+                sc.rec.dhi[k] = t.dhi[k];
+                sc.rec.dlo[k] = t.dlo[k];
+                }
+            sc.rec.ke = t.ke;
+            sc.rec.n_L = many ? 2ull : (gmin != ~0ull ? 1ull : 0ull);
+            sc.rec.first_L = gmin == ~0ull ? gmin : (gmin | (many ? MULTI_L_BIT : 0ull));
+            if (dbg)
+                dbg[6] = globaltimer_ns();
+            if (FINALIZE)
+                finalize<FORCE, BUSSI>(f, b, sc, scalars, publish);
+            if (dbg)
+                dbg[7] = globaltimer_ns();
             }
-        for (int k = 0; k < 3; k++)
-            {
-            sc.rec.dhi[k] = dh[k];
-            sc.rec.dlo[k] = dl[k];
-            }
-        sc.rec.ke = kes;
-        sc.rec.n_L = nL;
-        sc.rec.pad = 0;
-        sc.rec.pad_d = 0.0;
-        sc.rec.first_L = gmin;
         }
     __syncthreads();
     }
@@ -483,45 +726,48 @@ __device__ __forceinline__ void merge_phase(const Partial* __restrict__ recs, in
 // thread 0 only: merged record -> Final (shared) and, when `publish`, the device-resident Scalars
 template<bool FORCE, bool BUSSI>
 __device__ __forceinline__ void finalize(const ForceIn& f, const BussiIn& b, BlockScratch& sc, Scalars* scalars,
-                                         bool publish, int barrier_timeout)
+                                         bool publish)
     {
     const Partial& m = sc.rec;
     Final fin;
-    fin.n_L = m.n_L;
+    fin.many_L = 0;
     fin.has_photon = 0;
     fin.photon_local = -1;
     fin.Dq[0] = fin.Dq[1] = 0.0;
     fin.FL[0] = fin.FL[1] = fin.FL[2] = 0.0;
     fin.alpha = 1.0;
     fin.bussi_ok = 1;
+    fin.timeout = (int)(sc.flags & 1u);
     double en[3] = {0, 0, 0}, d[3] = {0, 0, 0}, q[3] = {0, 0, 0};
+    unsigned long long first = ~0ull;
     if (FORCE && m.first_L != ~0ull)
         {
         fin.has_photon = 1;
+        fin.many_L = (m.first_L & MULTI_L_BIT) != 0;
+        first = m.first_L & ~MULTI_L_BIT;
         const unsigned long long lo = f.index_offset;
-        if (m.first_L >= lo && m.first_L < lo + f.N)
-            fin.photon_local = (long long)(m.first_L - lo);
+        if (first >= lo && first < lo + f.N)
+            fin.photon_local = (long long)(first - lo);
+#pragma unroll
         for (int k = 0; k < 3; k++)
             {
             d[k] = __dadd_rn(m.dhi[k], m.dlo[k]);
             q[k] = m.q[k];
             }
-        const double g = f.g, K = f.K;
-        // CavityForceCompute.cc:174-176
+        // CavityForceCompute.cc:174-176; half_K = 0.5*K and half_g2K = 0.5*(g*g/K) from the host
         const double qq = __dadd_rn(__dadd_rn(__dmul_rn(q[0], q[0]), __dmul_rn(q[1], q[1])), __dmul_rn(q[2], q[2]));
         const double dq = __dadd_rn(__dadd_rn(__dmul_rn(d[0], q[0]), __dmul_rn(d[1], q[1])), 0.0);
         const double dd = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), 0.0);
-        en[0] = __dmul_rn(__dmul_rn(0.5, K), qq);
-        en[1] = __dmul_rn(g, dq);
-        en[2] = __dmul_rn(__dmul_rn(0.5, __ddiv_rn(__dmul_rn(g, g), K)), dd);
-        // :183
-        const double gk = __ddiv_rn(g, K);
-        fin.Dq[0] = __dadd_rn(q[0], __dmul_rn(gk, d[0]));
-        fin.Dq[1] = __dadd_rn(q[1], __dmul_rn(gk, d[1]));
+        en[0] = __dmul_rn(f.half_K, qq);
+        en[1] = __dmul_rn(f.g, dq);
+        en[2] = __dmul_rn(f.half_g2K, dd);
+        // :183, gk = g/K from the host
+        fin.Dq[0] = __dadd_rn(q[0], __dmul_rn(f.gk, d[0]));
+        fin.Dq[1] = __dadd_rn(q[1], __dmul_rn(f.gk, d[1]));
         // :203
-        fin.FL[0] = __dadd_rn(__dmul_rn(-K, q[0]), -__dmul_rn(g, d[0]));
-        fin.FL[1] = __dadd_rn(__dmul_rn(-K, q[1]), -__dmul_rn(g, d[1]));
-        fin.FL[2] = __dadd_rn(__dmul_rn(-K, q[2]), -__dmul_rn(g, 0.0));
+        fin.FL[0] = __dadd_rn(__dmul_rn(-f.K, q[0]), -__dmul_rn(f.g, d[0]));
+        fin.FL[1] = __dadd_rn(__dmul_rn(-f.K, q[1]), -__dmul_rn(f.g, d[1]));
+        fin.FL[2] = __dadd_rn(__dmul_rn(-f.K, q[2]), -__dmul_rn(f.g, 0.0));
         }
     double KE = 0.0, inst = 0.0;
     if (BUSSI)
@@ -548,8 +794,8 @@ __device__ __forceinline__ void finalize(const ForceIn& f, const BussiIn& b, Blo
                 }
             scalars->Dq[0] = fin.Dq[0];
             scalars->Dq[1] = fin.Dq[1];
-            scalars->photon_idx = fin.has_photon ? (long long)m.first_L : -1;
-            scalars->n_L = m.n_L;
+            scalars->photon_idx = fin.has_photon ? (long long)first : -1;
+            scalars->n_L = (unsigned int)m.n_L;
             }
         if (BUSSI)
             {
@@ -563,20 +809,9 @@ __device__ __forceinline__ void finalize(const ForceIn& f, const BussiIn& b, Blo
                     scalars->err = 1.0;
                 }
             }
-        if (barrier_timeout)
+        if (fin.timeout)
             scalars->err = 2.0;
         }
-    }
-
-template<bool FORCE, bool BUSSI>
-__device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, int G, const ForceIn& f,
-                                              const BussiIn& b, BlockScratch& sc, Scalars* scalars, bool publish,
-                                              int barrier_timeout)
-    {
-    merge_phase<FORCE, BUSSI>(recs, G, sc);
-    if (threadIdx.x == 0)
-        finalize<FORCE, BUSSI>(f, b, sc, scalars, publish, barrier_timeout);
-    __syncthreads();
     }
 
 // ------------------------------------------------------------------------------------------
@@ -588,7 +823,7 @@ __device__ __forceinline__ double4 force_of(unsigned long long i, double c, cons
     if (!fin.has_photon)
         return o; // CavityForceCompute.cc:149-156
     bool isL;
-    if (fin.n_L <= 1)
+    if (!fin.many_L)
         isL = (long long)i == fin.photon_local;
     else // several 'L' particles: the type has to be looked at again (32 B/particle, never in practice)
         isL = __double2loint(f.pos[i].w) == (int)f.L_typeid;
@@ -668,13 +903,71 @@ template<int UNROLL> __device__ __forceinline__ void apply_rescale(double alpha,
         }
     }
 
+// fused apply for a group [0, n): charge and velocity loads of U particles first, then the stores
+template<bool FORCE, bool RESCALE, int U>
+__device__ __forceinline__ void apply_stream(const Final& fin, const ForceIn& f, const BussiIn& b)
+    {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long nf = FORCE ? (unsigned long long)f.N : 0ull;
+    const unsigned long long nk = RESCALE ? (unsigned long long)b.n : 0ull;
+    const unsigned long long common = (FORCE && RESCALE) ? (nf < nk ? nf : nk) : (FORCE ? nf : nk);
+    const unsigned long long all = nf > nk ? nf : nk;
+    const double alpha = fin.alpha;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (U - 1) * stride < common; i += U * stride)
+        {
+        double c[FORCE ? U : 1];
+        double4 v[RESCALE ? U : 1];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            {
+            if (FORCE)
+                c[k] = __ldg(f.charge + i + k * stride);
+            if (RESCALE)
+                v[k] = ld256(b.vel + i + k * stride);
+            }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            {
+            const unsigned long long j = i + k * stride;
+            if (FORCE)
+                st256_stream(f.force + j, force_of(j, c[k], fin, f));
+            if (RESCALE)
+                {
+                v[k].x = __dmul_rn(v[k].x, alpha);
+                v[k].y = __dmul_rn(v[k].y, alpha);
+                v[k].z = __dmul_rn(v[k].z, alpha);
+                st256(b.vel + j, v[k]);
+                }
+            }
+        }
+    for (; i < all; i += stride)
+        {
+        if (FORCE && i < nf)
+            st256_stream(f.force + i, force_of(i, __ldg(f.charge + i), fin, f));
+        if (RESCALE && i < nk)
+            {
+            double4 v = ld256(b.vel + i);
+            v.x = __dmul_rn(v.x, alpha);
+            v.y = __dmul_rn(v.y, alpha);
+            v.z = __dmul_rn(v.z, alpha);
+            st256(b.vel + i, v);
+            }
+        }
+    }
+
 template<bool FORCE, bool BUSSI, int UNROLL>
 __device__ __forceinline__ void apply_phase(const Final& fin, const ForceIn& f, const BussiIn& b)
     {
-    if (FORCE)
-        apply_force<UNROLL>(fin, f);
-    if (BUSSI && b.rescale && fin.bussi_ok && fin.alpha != 1.0)
-        apply_rescale<UNROLL>(fin.alpha, b);
+    const bool rescale = BUSSI && b.rescale && fin.bussi_ok && fin.alpha != 1.0;
+    if (BUSSI && rescale && b.gidx == nullptr && b.first == 0)
+        apply_stream<FORCE, true, UNROLL>(fin, f, b);
+    else
+        {
+        if (FORCE)
+            apply_stream<true, false, UNROLL>(fin, f, b);
+        if (BUSSI && rescale)
+            apply_rescale<UNROLL>(fin.alpha, b);
+        }
     }
-
     } // namespace cavb

@@ -41,18 +41,19 @@ struct PeerTable
     };
 
 // kernel A
-template<int UNROLL>
-__global__ void __launch_bounds__(1024, 1)
+template<int UNROLL, int LB>
+__global__ void __launch_bounds__(LB, 1)
     k_shard_reduce(ForceIn f, BussiIn b, Partial* recs, unsigned long long* ticket, Partial* rank_record, int mode,
                    int rank, int nranks, unsigned long long seq, PeerTable peers)
     {
     __shared__ BlockScratch sc;
     __shared__ int s_last;
+    if (threadIdx.x == 0)
+        sc.flags = 0u;
     reduce_phase<true, true, UNROLL>(f, b, sc);
-    store_record(recs + blockIdx.x, sc.rec);
-    __syncthreads();
     if (threadIdx.x == 0)
         {
+        publish_record(recs + blockIdx.x, sc.rec, 0ull);
         __threadfence();
         const unsigned long long t = atom_acq_rel_add_u64(ticket, 1ull);
         s_last = (t == (unsigned long long)gridDim.x - 1);
@@ -60,23 +61,19 @@ __global__ void __launch_bounds__(1024, 1)
     __syncthreads();
     if (!s_last)
         return;
-    merge_phase<true, true>(recs, (int)gridDim.x, sc);
+    combine_phase<true, true, false, false>(recs, (int)gridDim.x, 0ull, f, b, sc, nullptr, false);
     if (threadIdx.x == 0)
         *ticket = 0ull;
     if (mode == 0)
         {
-        store_record(rank_record, sc.rec); // ncclAllGather sends it from here
+        if (threadIdx.x == 0)
+            publish_record(rank_record, sc.rec, 0ull); // ncclAllGather sends it from here
         return;
         }
-    // mode 1: one 16-byte word per (peer, word) pair, then one flag per peer
+    // mode 1: thread `peer` stores the five sectors into that peer's mailbox, then one flag per peer
     const int parity = (int)(seq & 1ull);
-    const double2* src = reinterpret_cast<const double2*>(&sc.rec);
-    for (int e = threadIdx.x; e < nranks * 8; e += blockDim.x)
-        {
-        const int peer = e >> 3, w = e & 7;
-        double2* dst = reinterpret_cast<double2*>(peers.mailbox[peer] + (size_t)parity * 16 + rank);
-        dst[w] = src[w];
-        }
+    if ((int)threadIdx.x < nranks)
+        publish_record(peers.mailbox[threadIdx.x] + (size_t)parity * 16 + rank, sc.rec, 0ull);
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < nranks)
@@ -84,22 +81,25 @@ __global__ void __launch_bounds__(1024, 1)
     }
 
 // kernel B
-template<int UNROLL>
-__global__ void __launch_bounds__(1024, 1)
+template<int UNROLL, int LB>
+__global__ void __launch_bounds__(LB, 1)
     k_shard_apply(ForceIn f, BussiIn b, const Partial* gathered, Scalars* scalars, int mode, int nranks,
                   unsigned long long seq, const unsigned long long* my_flags)
     {
     __shared__ BlockScratch sc;
     __shared__ int s_timeout;
     if (threadIdx.x == 0)
+        {
         s_timeout = 0;
+        sc.flags = 0u;
+        }
     __syncthreads();
     if (mode == 1 && (int)threadIdx.x < nranks)
         {
         const unsigned long long t0 = globaltimer_ns();
         while (ld_acquire_sys_u64(my_flags + threadIdx.x) < seq)
             {
-            if (globaltimer_ns() - t0 > 2000000000ull) // 2 s: never hang the GPU
+            if (globaltimer_ns() - t0 > 2000000000ull) // 2 s (peers may start late): never hang the GPU
                 {
                 s_timeout = 1;
                 break;
@@ -107,10 +107,11 @@ __global__ void __launch_bounds__(1024, 1)
             }
         }
     __syncthreads();
-    const int timeout = s_timeout;
+    if (threadIdx.x == 0 && s_timeout)
+        sc.flags = 1u;
     const Partial* recs = gathered + (mode == 1 ? (size_t)(seq & 1ull) * 16 : 0);
-    combine_phase<true, true>(recs, nranks, f, b, sc, scalars, blockIdx.x == 0, timeout);
-    if (timeout)
+    combine_phase<true, true, false, true>(recs, nranks, 0ull, f, b, sc, scalars, blockIdx.x == 0);
+    if (sc.fin.timeout)
         return;
     apply_phase<true, true, UNROLL>(sc.fin, f, b);
     }
@@ -164,13 +165,13 @@ static int ensure_mailbox(cavb200_handle* h)
     return 0;
     }
 
-template<int UNROLL> static int launch_shard_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaStream_t s)
+template<int UNROLL, int LB> static int launch_shard_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaStream_t s)
     {
     ShardState& sh = h->shard;
     int rc = ensure_mailbox(h);
     if (rc)
         return rc;
-    const int threads = h->tune.threads;
+    const int threads = h->tune.threads > LB ? LB : h->tune.threads;
     const unsigned long long work = f.N > b.n ? f.N : b.n;
     unsigned long long want = (work + threads - 1) / threads;
     if (want < 1)
@@ -194,7 +195,7 @@ template<int UNROLL> static int launch_shard_t(cavb200_handle* h, const ForceIn&
         peers.flags[0] = sh.flags;
         }
     Partial* rank_record = h->partials + MAX_PARTIALS - 1;
-    k_shard_reduce<UNROLL><<<grid, threads, 0, s>>>(f, b, h->partials, h->counters + 4, rank_record, mode, sh.rank, nranks,
+    k_shard_reduce<UNROLL, LB><<<grid, threads, 0, s>>>(f, b, h->partials, h->counters + 4, rank_record, mode, sh.rank, nranks,
                                                      sh.seq, peers);
     CAVB_CHECK(cudaGetLastError());
     if (mode == 0)
@@ -205,7 +206,7 @@ template<int UNROLL> static int launch_shard_t(cavb200_handle* h, const ForceIn&
         if (api->AllGather(rank_record, sh.gather, sizeof(Partial), ncclChar, (ncclComm_t)sh.nccl_comm, s) != ncclSuccess)
             return (int)cudaErrorUnknown;
         }
-    k_shard_apply<UNROLL><<<grid, threads, 0, s>>>(f, b, sh.gather, h->scalars, mode, nranks, sh.seq, sh.flags);
+    k_shard_apply<UNROLL, LB><<<grid, threads, 0, s>>>(f, b, sh.gather, h->scalars, mode, nranks, sh.seq, sh.flags);
     CAVB_CHECK(cudaGetLastError());
     h->launches += 2;
     return 0;
@@ -215,12 +216,12 @@ int launch_shard_step(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cud
     {
     switch (h->tune.unroll)
         {
-    case 1:
-        return launch_shard_t<1>(h, *f, *b, s);
+    case 8:
+        return launch_shard_t<8, 256>(h, *f, *b, s);
     case 4:
-        return launch_shard_t<4>(h, *f, *b, s);
+        return launch_shard_t<4, 512>(h, *f, *b, s);
     default:
-        return launch_shard_t<2>(h, *f, *b, s);
+        return launch_shard_t<2, 1024>(h, *f, *b, s);
         }
     }
     } // namespace cavb
@@ -369,17 +370,14 @@ int cavb200_shard_step(cavb200_handle* h, const double* pos, const double* charg
     f.L_typeid = L_typeid;
     f.g = params->couplstr;
     f.K = params->K;
+    fill_force_constants(f);
     BussiIn b;
     b.vel = reinterpret_cast<double4*>(vel);
     b.gidx = nullptr;
     b.first = group_first;
     b.n = n_group;
     b.rescale = bussi->deltaT != 0.0;
-    b.kT = bussi->kT;
-    b.dof = bussi->dof;
-    b.r_normal = bussi->r_normal;
-    b.c = (bussi->tau != 0.0) ? exp(-bussi->deltaT / bussi->tau) : 0.0;
-    b.r_gamma = (bussi->dof > 1.0) ? 2.0 * bussi->gamma_draw : 0.0;
+    fill_bussi_constants(b, bussi);
     return launch_shard_step(h, &f, &b, (cudaStream_t)stream);
     }
     }

@@ -83,6 +83,9 @@ int cavb200_destroy(cavb200_handle* h);
 const char* cavb200_error_string(int err);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t cavb200_launch_count(const cavb200_handle* h);
+/* Debug: with tuning "stamps" = 1 the cooperative kernel records, per CTA, globaltimer ns at
+ * {start, after reduce, after barrier, after combine, after apply}; out = uint64[8*n_ctas]. */
+int cavb200_debug_stamps(cavb200_handle* h, uint64_t* out, uint32_t n_ctas);
 /* Tuning knobs ("force_ctas_per_sm", "force_threads", "variant", ...); unknown key -> 1. */
 int cavb200_set_tuning(cavb200_handle* h, const char* key, int value);
 int cavb200_get_tuning(const cavb200_handle* h, const char* key, int* value);
@@ -153,10 +156,10 @@ int cavb200_fkt(cavb200_handle* h, const double* rho, uint32_t T, uint32_t K, ui
  * New functionality (the reference never reduces across ranks): each rank holds a
  * contiguous block of particles; between the reduce pass and the apply pass the ranks combine
  * {d (compensated pairs), first-photon index and position, KE} in rank-ascending order.
- *   mode 0: ncclAllGather of the 128-byte per-rank record (libnccl resolved with dlopen)
+ *   mode 0: ncclAllGather of the 160-byte per-rank record (libnccl resolved with dlopen)
  *   mode 1: one-shot NVLink exchange -- the reduce kernel's last block stores the record into
  *           every peer's mailbox (CUDA IPC peer memory) and the apply kernel spins on its own. */
-#define CAVB200_SHARD_RECORD_BYTES 128
+#define CAVB200_SHARD_RECORD_BYTES 160
 #define CAVB200_NCCL_UNIQUE_ID_BYTES 128
 int cavb200_shard_nccl_unique_id(void* out128);
 int cavb200_shard_init_nccl(cavb200_handle* h, const void* unique_id128, int rank, int nranks);

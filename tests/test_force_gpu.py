@@ -69,7 +69,7 @@ def test_force_grid(handle, coracle, n_mol, variant):
 @pytest.mark.parametrize("photon", PHOTON)
 @pytest.mark.parametrize("n_mol", [1, 33, 1000, 100001])
 def test_force_photon_placement(handle, coracle, n_mol, photon, variant):
-    handle.set_tuning(variant=variant, threads=256, ctas_per_sm=4, unroll=1)
+    handle.set_tuning(variant=variant, threads=256, ctas_per_sm=1, unroll=8)
     s = synth.make_system(n_mol, photon=photon)
     ref = coracle.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, OMEGAC, G)
     exact = coracle.dipole_exact(s.pos, s.charge, s.image, s.box, ref["photon_idx"])
@@ -134,8 +134,8 @@ def test_force_deterministic_and_idempotent(handle):
     assert np.array_equal(a["dipole"], b["dipole"])
 
 
-@pytest.mark.parametrize("threads,ctas,unroll,variant", [(256, 4, 1, 1), (1024, 1, 2, 1), (512, 1, 4, 1), (512, 2, 4, 0),
-                                                         (128, 8, 2, 0)])
+@pytest.mark.parametrize("threads,ctas,unroll,variant", [(256, 4, 2, 1), (1024, 1, 2, 1), (512, 1, 4, 1), (512, 2, 4, 0),
+                                                         (128, 8, 2, 0), (256, 1, 8, 1), (128, 2, 8, 0)])
 def test_force_launch_shapes(handle, coracle, threads, ctas, unroll, variant):
     handle.set_tuning(variant=variant, threads=threads, ctas_per_sm=ctas, unroll=unroll)
     s = synth.make_system(200003)

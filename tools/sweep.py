@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default="")
+    ap.add_argument("--pdl", type=int, default=1)
     args = ap.parse_args()
     peak = 6454.9
     try:
@@ -62,16 +63,17 @@ def main():
         e1.record(st.ptr)
         return e1.elapsed_ms_since(e0) / steps
 
-    shapes = [(v, t, c, u) for v in (1, 0) for (t, c) in ((256, 4), (512, 2), (1024, 1), (512, 1), (256, 2), (256, 8), (128, 8))
-              for u in (1, 2, 4)]
+    shapes = [(v, t, c, u) for v in (1, 0) for (t, c, u) in ((384, 2, 2), (320, 2, 2), (256, 3, 2), (512, 2, 2), (1024, 1, 2), (256, 4, 2), (512, 1, 2), (512, 1, 4),
+                                                             (256, 2, 4), (256, 1, 4), (384, 1, 4), (256, 1, 8), (192, 1, 8),
+                                                             (128, 1, 8), (128, 2, 8))]
     if args.quick:
-        shapes = [(1, 512, 2, 2), (0, 512, 2, 2), (1, 1024, 1, 2), (1, 256, 4, 2)]
+        shapes = [(1, 384, 2, 2), (0, 384, 2, 2), (1, 1024, 1, 2), (1, 512, 1, 4)]
     rows = []
     print(f"N={N} systems={len(systems)} peak={peak} GB/s")
     print("variant threads ctas unroll | force_us frac | bussi_us frac | step_us frac | force+bussi_us frac")
     for v, t, c, u in shapes:
         try:
-            h.set_tuning(variant=v, threads=t, ctas_per_sm=c, unroll=u)
+            h.set_tuning(variant=v, threads=t, ctas_per_sm=c, unroll=u, pdl=args.pdl)
             res = {}
             for kind, nbytes in (("force", 84 * N), ("bussi", 64 * n_mol), ("step", 84 * N + 64 * n_mol),
                                  ("both", 84 * N + 64 * n_mol)):
