@@ -65,6 +65,8 @@ _SIGNATURES = {
     "cavb200_bussi_read": (C.c_int, [_vp, _dp, _vp]),
     "cavb200_bussi_reset": (C.c_int, [_vp, _vp]),
     "cavb200_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _u32, _u32, _BP, _vp]),
+    "cavb200_nve_kick_drift": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _dbl, _vp]),
+    "cavb200_nve_half_kick": (C.c_int, [_vp, _vp, _vp, _u32, _dbl, _vp]),
     "cavb200_rhok": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _u32, _vp, _u32, _vp, _vp]),
     "cavb200_fkt": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp]),
     "cavb200_shard_nccl_unique_id": (C.c_int, [_vp]),
@@ -347,6 +349,14 @@ class Handle:
                                          box[0], box[1], box[2], L_typeid & 0xFFFFFFFF, C.byref(params), group_first,
                                          n_group, C.byref(bussi), en, bo), "cavb200_step_host")
         return np.array(en[:]), dict(ke=bo[0], alpha=bo[1], instantaneous=bo[2], cumulative=bo[3], err=bo[4])
+
+    # -- NVE harness ------------------------------------------------------------------------------
+    def nve_kick_drift(self, pos, vel, force, N, dt, stream=None):
+        check(self.lib.cavb200_nve_kick_drift(self.h, _ptr(pos), _ptr(vel), _ptr(force), N, dt, stream),
+              "cavb200_nve_kick_drift")
+
+    def nve_half_kick(self, vel, force, N, dt, stream=None):
+        check(self.lib.cavb200_nve_half_kick(self.h, _ptr(vel), _ptr(force), N, dt, stream), "cavb200_nve_half_kick")
 
     # -- F(k,t) ----------------------------------------------------------------------------------
     def rhok(self, pos, stride, frame_stride, N, T, kvec, K, rho, stream=None):

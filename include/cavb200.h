@@ -138,6 +138,16 @@ int cavb200_step(cavb200_handle* h, const double* pos, const double* charge, con
                  uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
                  uint32_t n_group, const cavb200_bussi_args* bussi, void* stream);
 
+/* ---- minimal NVE harness (velocity Verlet around the cavity force) ------------------------------
+ * Not a reference function: the step harness the 10k-step energy-drift comparison of
+ * BASELINE.json runs on both arms (oracle: orc_nve_step).  Masses are vel.w; positions are NOT
+ * wrapped and images are not touched.
+ *   kick_drift:  v += (dt/2) f/m;  r += dt v        half_kick:  v += (dt/2) f/m
+ *   kinetic:     writes sum 1/2 m |v|^2 over all N particles to the Bussi KE slot (cavb200_bussi_read) */
+int cavb200_nve_kick_drift(cavb200_handle* h, double* pos, double* vel, const double* force, uint32_t N, double dt,
+                           void* stream);
+int cavb200_nve_half_kick(cavb200_handle* h, double* vel, const double* force, uint32_t N, double dt, void* stream);
+
 /* ---- F(k,t): density field --------------------------------------------------------------------
  * rho[t][k] = sum_j exp(i kvec[k] . r_j(t)) over ALL N particles of frame t (wrapped positions),
  * the batched form of compute_density_field (reference src/cavitymd/analysis.py:34-47).
