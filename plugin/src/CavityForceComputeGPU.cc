@@ -1,0 +1,140 @@
+// CavityForceComputeGPU.cc -- see the header.  No CPU fallback: a failure of the CUDA path throws.
+#include "CavityForceComputeGPU.h"
+
+#include <stdexcept>
+#include <string>
+
+namespace hoomd
+    {
+namespace cavitymd
+    {
+namespace
+    {
+void check(int err, const char* what)
+    {
+    if (err != 0)
+        throw std::runtime_error(std::string("CavityForceComputeGPU: ") + what + ": " + cavb200_error_string(err));
+    }
+    } // namespace
+
+CavityForceComputeGPU::CavityForceComputeGPU(std::shared_ptr<SystemDefinition> sysdef, Scalar omegac, Scalar couplstr,
+                                             Scalar phmass)
+    : ForceCompute(sysdef), m_handle(nullptr), m_fresh(true)
+    {
+    m_exec_conf->msg->notice(5) << "Constructing CavityForceComputeGPU (cavb200)" << std::endl;
+    if (!m_exec_conf->isCUDAEnabled())
+        throw std::runtime_error("CavityForceComputeGPU requires a GPU execution configuration (no CPU fallback)");
+    setParams(omegac, couplstr, phmass);
+    for (int k = 0; k < 3; k++)
+        m_energies[k] = m_dipole[k] = 0.0;
+    int device = 0;
+#ifdef ENABLE_HIP
+    cudaGetDevice(&device);
+#endif
+    check(cavb200_create(&m_handle, device), "cavb200_create");
+    }
+
+CavityForceComputeGPU::~CavityForceComputeGPU()
+    {
+    m_exec_conf->msg->notice(5) << "Destroying CavityForceComputeGPU" << std::endl;
+    cavb200_destroy(m_handle);
+    }
+
+void CavityForceComputeGPU::setParams(Scalar omegac, Scalar couplstr, Scalar phmass)
+    {
+    m_params.omegac = omegac;
+    m_params.couplstr = couplstr;
+    m_params.phmass = phmass;
+    m_params.K = phmass * omegac * omegac; // reference src/CavityForceCompute.h:38-42
+    }
+
+pybind11::dict CavityForceComputeGPU::getParams()
+    {
+    pybind11::dict v;
+    v["omegac"] = m_params.omegac;
+    v["couplstr"] = m_params.couplstr;
+    v["K"] = m_params.K;
+    v["phmass"] = m_params.phmass;
+    return v;
+    }
+
+void CavityForceComputeGPU::computeForces(uint64_t timestep)
+    {
+    (void)timestep;
+    const unsigned int N = m_pdata->getN();
+    // 'L' missing from the type list: the reference GPU class reports zero energies and leaves the
+    // forces zero (src/CavityForceComputeGPU.cc:114-123); UINT32_MAX asks the library for exactly that
+    uint32_t L_typeid = 0xFFFFFFFFu;
+    try
+        {
+        L_typeid = m_pdata->getTypeByName("L");
+        }
+    catch (...)
+        {
+        }
+    const BoxDim box = m_pdata->getGlobalBox();
+    const Scalar3 L = box.getL();
+
+    ArrayHandle<Scalar4> d_pos(m_pdata->getPositions(), access_location::device, access_mode::read);
+    ArrayHandle<Scalar> d_charge(m_pdata->getCharges(), access_location::device, access_mode::read);
+    ArrayHandle<int3> d_image(m_pdata->getImages(), access_location::device, access_mode::read);
+    ArrayHandle<Scalar4> d_force(m_force, access_location::device, access_mode::overwrite);
+
+    // HOOMD runs its kernels on the legacy default stream: stream 0 ordering is the contract
+    check(cavb200_force(m_handle, reinterpret_cast<const double*>(d_pos.data), d_charge.data,
+                        reinterpret_cast<const int32_t*>(d_image.data), reinterpret_cast<double*>(d_force.data), N, L.x,
+                        L.y, L.z, L_typeid, &m_params, nullptr),
+          "cavb200_force");
+    m_fresh = false; // no synchronisation here: energies are fetched when somebody asks
+    }
+
+void CavityForceComputeGPU::readBack()
+    {
+    if (m_fresh)
+        return;
+    int32_t photon = -1;
+    check(cavb200_force_read(m_handle, m_energies, m_dipole, &photon, nullptr), "cavb200_force_read");
+    m_fresh = true;
+    }
+
+Scalar CavityForceComputeGPU::getHarmonicEnergy()
+    {
+    readBack();
+    return m_energies[0];
+    }
+Scalar CavityForceComputeGPU::getCouplingEnergy()
+    {
+    readBack();
+    return m_energies[1];
+    }
+Scalar CavityForceComputeGPU::getDipoleSelfEnergy()
+    {
+    readBack();
+    return m_energies[2];
+    }
+pybind11::tuple CavityForceComputeGPU::getDipole()
+    {
+    readBack();
+    return pybind11::make_tuple(m_dipole[0], m_dipole[1], m_dipole[2]);
+    }
+
+namespace detail
+    {
+void export_CavityForceComputeGPU(pybind11::module& m)
+    {
+    // same python-visible name, constructor and methods as the reference export
+    // (src/CavityForceComputeGPU.cc:257-265 + the base-class methods of src/CavityForceCompute.cc:212-224)
+    pybind11::class_<CavityForceComputeGPU, ForceCompute, std::shared_ptr<CavityForceComputeGPU>>(m, "CavityForceComputeGPU")
+        .def(pybind11::init<std::shared_ptr<SystemDefinition>, Scalar, Scalar, Scalar>(), pybind11::arg("sysdef"),
+             pybind11::arg("omegac"), pybind11::arg("couplstr"), pybind11::arg("phmass") = 1.0)
+        .def("setParams", &CavityForceComputeGPU::setParams, pybind11::arg("omegac"), pybind11::arg("couplstr"),
+             pybind11::arg("phmass") = 1.0)
+        .def("getParams", &CavityForceComputeGPU::getParams)
+        .def("getHarmonicEnergy", &CavityForceComputeGPU::getHarmonicEnergy)
+        .def("getCouplingEnergy", &CavityForceComputeGPU::getCouplingEnergy)
+        .def("getDipoleSelfEnergy", &CavityForceComputeGPU::getDipoleSelfEnergy)
+        .def("getDipole", &CavityForceComputeGPU::getDipole);
+    }
+    } // namespace detail
+    } // namespace cavitymd
+    } // namespace hoomd

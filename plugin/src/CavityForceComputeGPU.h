@@ -1,0 +1,60 @@
+// CavityForceComputeGPU.h -- B200 host class of the cavity force.
+//
+// Drop-in for the reference's class of the same name (reference src/CavityForceComputeGPU.h:30-56):
+// same constructor (sysdef, omegac, couplstr, phmass = 1), same pybind name, same methods
+// (setParams, getParams, getHarmonicEnergy, getCouplingEnergy, getDipoleSelfEnergy), still a
+// hoomd::ForceCompute whose computeForces(timestep) HOOMD's integrator calls once per step.
+// What changed is everything below that boundary: instead of four GPUArray workspaces, per-step
+// memsets, a C++ kernel driver, two blocking D2H copies, a device synchronize and two full-array
+// host read-backs (reference src/CavityForceComputeGPU.cc:102-253), computeForces borrows HOOMD's
+// device pointers and makes ONE asynchronous call into the C ABI (include/cavb200.h).  Energies stay
+// on the device until a getter asks for them.
+#ifndef CAVB200_CAVITY_FORCE_COMPUTE_GPU_H
+#define CAVB200_CAVITY_FORCE_COMPUTE_GPU_H
+
+#include "hoomd/ForceCompute.h"
+#include "hoomd/HOOMDMath.h"
+
+#include <cavb200.h>
+#include <memory>
+#include <pybind11/pybind11.h>
+
+namespace hoomd
+    {
+namespace cavitymd
+    {
+class PYBIND11_EXPORT CavityForceComputeGPU : public ForceCompute
+    {
+    public:
+    CavityForceComputeGPU(std::shared_ptr<SystemDefinition> sysdef, Scalar omegac, Scalar couplstr,
+                          Scalar phmass = Scalar(1.0));
+    virtual ~CavityForceComputeGPU();
+
+    //! K = phmass * omegac * omegac, as the reference's cavity_force_params constructor forms it
+    void setParams(Scalar omegac, Scalar couplstr, Scalar phmass = Scalar(1.0));
+    pybind11::dict getParams();
+    Scalar getHarmonicEnergy();
+    Scalar getCouplingEnergy();
+    Scalar getDipoleSelfEnergy();
+    //! total molecular dipole of the last step (not in the reference API; free with the reduction)
+    pybind11::tuple getDipole();
+
+    protected:
+    virtual void computeForces(uint64_t timestep);
+
+    private:
+    void readBack();
+    cavb200_handle* m_handle;
+    cavb200_params m_params;
+    double m_energies[3];
+    double m_dipole[3];
+    bool m_fresh; //!< host copies are current
+    };
+
+namespace detail
+    {
+void export_CavityForceComputeGPU(pybind11::module& m);
+    }
+    } // namespace cavitymd
+    } // namespace hoomd
+#endif

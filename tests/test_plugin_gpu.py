@@ -1,0 +1,118 @@
+"""The plugin glue (plugin/src: CavityForceComputeGPU, BussiReservoirThermostat -- the pybind11 /
+HOOMD host classes that call the C ABI) built against hoomd_shim and driven the way HOOMD's
+integrator drives them: ForceCompute.compute(timestep) and Thermostat.getRescalingFactorsOne(
+timestep, dt).  Same class names, constructors and methods as the reference's _cavitymd /
+_bussi_reservoir modules."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from cav_hoomd_b200 import synth
+
+pytestmark = pytest.mark.gpu
+BUILD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "plugin", "build")
+
+
+@pytest.fixture(scope="module")
+def mods():
+    sys.path.insert(0, BUILD)
+    import _hoomd_shim  # noqa: F401  (registers ForceCompute / Thermostat bases first)
+    import _bussi_reservoir
+    import _cavitymd
+    return _hoomd_shim, _cavitymd, _bussi_reservoir
+
+
+def make_sysdef(shim, s, seed=7):
+    exec_conf = shim.ExecutionConfiguration(True, 0)
+    pd = shim.ParticleData(s.N, s.box[0], s.box[1], s.box[2], list(s.types), exec_conf)
+    pd.setPositions(s.pos)
+    pd.setVelocities(s.vel)
+    pd.setCharges(s.charge)
+    pd.setImages(s.image)
+    return shim.SystemDefinition(pd, seed), pd
+
+
+def test_cavity_force_compute_gpu_class(mods, coracle):
+    shim, cav, _ = mods
+    s = synth.make_system(30000)
+    sysdef, pd = make_sysdef(shim, s)
+    fc = cav.CavityForceComputeGPU(sysdef, 0.01, 1e-3)  # (sysdef, omegac, couplstr, phmass=1.0)
+    p = fc.getParams()
+    assert p["omegac"] == 0.01 and p["couplstr"] == 1e-3 and p["phmass"] == 1.0 and p["K"] == 1.0 * 0.01 * 0.01
+    assert fc.getHarmonicEnergy() == 0.0  # before the first compute
+    fc.compute(0)
+    ref = coracle.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, 0.01, 1e-3)
+    f = fc.getForces()
+    assert np.abs(f - ref["force"]).max() <= 1e-10 * np.abs(ref["force"]).max()
+    assert np.isclose(fc.getHarmonicEnergy(), ref["energies"][0], rtol=1e-10)
+    assert np.isclose(fc.getCouplingEnergy(), ref["energies"][1], rtol=1e-10)
+    assert np.isclose(fc.getDipoleSelfEnergy(), ref["energies"][2], rtol=1e-10)
+    assert fc.calcEnergySum() == 0.0  # per-particle PE stays 0 (reference CavityForceCompute.cc:178-180)
+    # setParams takes effect on the next compute
+    fc.setParams(0.01, 2e-3, 1.0)
+    fc.compute(1)
+    ref2 = coracle.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, 0.01, 2e-3)
+    assert np.isclose(fc.getCouplingEnergy(), ref2["energies"][1], rtol=1e-10)
+
+
+def test_cavity_force_requires_gpu_exec_conf(mods):
+    shim, cav, _ = mods
+    s = synth.make_system(10)
+    pd = shim.ParticleData(s.N, 1, 1, 1, list(s.types), shim.ExecutionConfiguration(False, 0))
+    with pytest.raises(RuntimeError):
+        cav.CavityForceComputeGPU(shim.SystemDefinition(pd, 0), 0.01, 1e-3)  # no CPU fallback
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_bussi_reservoir_thermostat_class(mods, coracle, fused):
+    shim, _, bus = mods
+    n = 4000
+    s = synth.make_system(n)
+    sysdef, pd = make_sysdef(shim, s)
+    group = shim.ParticleGroup(sysdef, list(range(n)))
+    dof = 3.0 * n - 3.0
+    group.setTranslationalDOF(dof)
+    thermo = shim.ComputeThermo(sysdef, group)
+    kT = shim.VariantConstant(synth.KT_100K)
+    th = bus.BussiReservoirThermostat(kT, group, thermo, sysdef, synth.TAU_5PS)
+    assert th.tau == synth.TAU_5PS and th.kT(0) == synth.KT_100K
+    assert th.getTotalReservoirEnergy() == 0.0 and th.getReservoirEnergyRotational() == 0.0
+    th.fused_rescale = fused
+    assert th.getRescalingFactorsOne(0, 0.0) == [1.0, 1.0]  # deltaT == 0 (reference :45-48)
+
+    vref = s.vel.copy()
+    res = np.zeros(2)
+    idx = np.arange(n, dtype=np.uint32)
+    rng = np.random.default_rng(3)
+    for t in range(4):
+        r, g = rng.standard_normal(), rng.gamma((dof - 1) / 2)
+        bus._inject_draws([r, g])
+        factors = th.getRescalingFactorsOne(t, synth.DT_1FS)
+        alpha, ke = coracle.bussi_step(vref, idx, dof, synth.DT_1FS, synth.KT_100K, synth.TAU_5PS, r, g, res)
+        if fused:
+            assert factors == [1.0, 1.0]  # the kernel already rescaled
+        else:
+            assert abs(factors[0] - alpha) <= 1e-12 * abs(alpha) and factors[1] == 1.0
+            v = pd.getVelocities()  # what HOOMD's step one does with the factor
+            v[:n, :3] *= factors[0]
+            pd.setVelocities(v)
+        assert np.isclose(th.getInstantaneousReservoirTranslational(), res[1], rtol=1e-9, atol=1e-18)
+    assert np.isclose(th.getTotalReservoirEnergy(), res[0], rtol=1e-9, atol=1e-18)
+    assert np.allclose(pd.getVelocities(), vref, rtol=1e-11, atol=0)
+    th.resetReservoirEnergy()
+    assert th.getTotalReservoirEnergy() == 0.0 and th.getInstantaneousReservoirTotal() == 0.0
+
+
+def test_bussi_thermostat_zero_momenta_throws(mods):
+    shim, _, bus = mods
+    s = synth.make_system(100)
+    s.vel[:, :3] = 0.0
+    sysdef, pd = make_sysdef(shim, s)
+    group = shim.ParticleGroup(sysdef, list(range(100)))
+    group.setTranslationalDOF(297.0)
+    th = bus.BussiReservoirThermostat(shim.VariantConstant(1.0), group, shim.ComputeThermo(sysdef, group), sysdef, 1.0)
+    bus._inject_draws([0.1, 140.0])
+    with pytest.raises(RuntimeError, match="non-zero initial momenta"):
+        th.getRescalingFactorsOne(0, 0.005)
