@@ -73,7 +73,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -85,7 +85,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -282,8 +282,8 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.1)  # let nvidia-smi start before the timed region
     ms_fused, launches_fused = timed(True, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
     ms_sep, launches = timed(False, args.steps, args.warmup + args.steps)
 
     # per-kernel durations, CUDA events on the launching stream around every launch:
@@ -309,6 +309,7 @@ def run_b200(args):
     capi.sync()
     t_force = float(np.mean([b.elapsed_ms_since(a) for a, b, c in evs]))
     t_bussi = float(np.mean([c.elapsed_ms_since(b) for a, b, c in evs]))
+    clocks = sampler.stop() if rank == 0 else None  # sampled from before the timed regions to here
 
     # e2e: host-buffer C-ABI call, pinned host arrays, copies inside the timed region
     e2e_steps = max(3, min(args.steps, 20))
@@ -392,7 +393,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-mol", type=int, default=1_000_000)
