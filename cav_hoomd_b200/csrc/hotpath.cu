@@ -93,6 +93,63 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         my_stamps[4] = globaltimer_ns();
     }
 
+// variant 2 ("split-phase"): the thermostat half and the force half are independent, so their two
+// hand-offs can hide behind each other's streaming instead of idling the machine:
+//     dipole reduce -> publish | KE reduce -> publish | take Dq (arrived long ago) -> forces |
+//     take alpha (arrived during the force writes) -> rescale
+// No CTA ever waits for the slowest CTA of the phase it has just finished.  Measured background
+// (profiles/microwb_r1b.txt): the read half is HBM bound, the write half is bound by L2 store
+// ingest with HBM idle, so a CTA that runs ahead into its write half does not slow the readers.
+template<int UNROLL, int LB>
+__global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
+    k_split(ForceIn f, BussiIn b, Partial* recsF, Partial* recsB, Scalars* scalars, unsigned long long* epoch_ctr,
+            unsigned long long* stamps)
+    {
+    __shared__ BlockScratch sc;
+    unsigned long long* my_stamps = (stamps && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
+    if (my_stamps)
+        my_stamps[0] = globaltimer_ns();
+    pdl_wait();
+    if (threadIdx.x == 0)
+        {
+        sc.flags = 0u;
+        sc.epoch = ld_relaxed_u64(epoch_ctr) + 1ull;
+        }
+    // dipole first: its hand-off (the heavier combine, and the one whose stragglers matter) then has
+    // the whole velocity pass to complete behind; the light KE hand-off hides behind the force writes
+    reduce_phase<true, false, UNROLL>(f, b, sc);
+    const unsigned long long epoch = sc.epoch;
+    if (threadIdx.x == 0)
+        publish_record(recsF + blockIdx.x, sc.rec, epoch);
+    if (my_stamps)
+        my_stamps[1] = globaltimer_ns();
+    reduce_phase<false, true, UNROLL>(f, b, sc);
+    if (threadIdx.x == 0)
+        publish_record(recsB + blockIdx.x, sc.rec, epoch);
+    if (my_stamps)
+        my_stamps[2] = globaltimer_ns();
+    combine_phase<true, false, true, true>(recsF, (int)gridDim.x, epoch, f, b, sc, scalars, blockIdx.x == 0);
+    if (my_stamps)
+        my_stamps[3] = globaltimer_ns();
+    const bool timeout_f = sc.fin.timeout != 0;
+    if (!timeout_f)
+        apply_phase<true, false, UNROLL>(sc.fin, f, b);
+    if (my_stamps)
+        my_stamps[4] = globaltimer_ns();
+    __syncthreads(); // sc.fin / sc.rec are rewritten by the second combine
+    combine_phase<false, true, true, true>(recsB, (int)gridDim.x, epoch, f, b, sc, scalars, blockIdx.x == 0);
+    if (my_stamps)
+        my_stamps[5] = globaltimer_ns();
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        *epoch_ctr = epoch; // every CTA has published twice, hence read the counter
+    if (sc.fin.timeout || timeout_f)
+        return;
+    pdl_launch_dependents();
+    apply_phase<false, true, UNROLL>(sc.fin, f, b);
+    if (my_stamps)
+        my_stamps[6] = globaltimer_ns();
+    }
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -113,7 +170,48 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         max_grid = MAX_PARTIALS;
     Final* fin_dev = reinterpret_cast<Final*>(h->counters + 8);
 
-    if (h->tune.variant == 1 && h->coop_supported)
+    if (FORCE && BUSSI && h->tune.variant == 2 && h->coop_supported && b.rescale)
+        {
+        int per_sm = 0;
+        CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split<UNROLL, LB>, threads, 0));
+        if (per_sm < 1)
+            return (int)cudaErrorLaunchOutOfResources;
+        if (max_grid > per_sm * h->num_sms)
+            max_grid = per_sm * h->num_sms;
+        if (max_grid > MAX_PARTIALS / 2)
+            max_grid = MAX_PARTIALS / 2;
+        const int grid = (int)(want < (unsigned long long)max_grid ? want : (unsigned long long)max_grid);
+        Partial* recsF = h->partials;
+        Partial* recsB = h->partials + MAX_PARTIALS / 2;
+        Scalars* sca = h->scalars;
+        unsigned long long* arr = h->counters + 2;
+        ForceIn ff = f;
+        BussiIn bb = b;
+        unsigned long long* stamps = h->tune.stamps ? h->stamps : nullptr;
+        void* args[] = {&ff, &bb, &recsF, &recsB, &sca, &arr, &stamps};
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(threads);
+        cfg.stream = s;
+        cudaLaunchAttribute attrs[1];
+        if (h->tune.pdl)
+            {
+            attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attrs[0].val.programmaticStreamSerializationAllowed = 1;
+            }
+        else
+            {
+            attrs[0].id = cudaLaunchAttributeCooperative;
+            attrs[0].val.cooperative = 1;
+            }
+        cfg.attrs = attrs;
+        cfg.numAttrs = 1;
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_split<UNROLL, LB>, args));
+        h->launches += 1;
+        return 0;
+        }
+
+    if (h->tune.variant >= 1 && h->coop_supported)
         {
         int per_sm = 0;
         CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<FORCE, BUSSI, UNROLL, LB>, threads, 0));
@@ -211,6 +309,8 @@ static int launch_u(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         // to the 64-register build
         if (h->tune.threads <= 384)
             return launch_t<FORCE, BUSSI, 2, 384>(h, f, b, s);
+        if (h->tune.threads <= 768) // one 768-thread CTA per SM: same 80-register budget, half the records
+            return launch_t<FORCE, BUSSI, 2, 768>(h, f, b, s);
         return launch_t<FORCE, BUSSI, 2, 1024>(h, f, b, s);
         }
     }

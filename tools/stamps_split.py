@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""tools/stamps_split.py -- variant 2 (split-phase kernel): bitwise check against variant 1, per-CTA
+phase stamps and back-to-back step time."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cav_hoomd_b200 import capi, synth  # noqa: E402
+from tools.prof_step import call, make  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-mol", type=int, default=1_000_000)
+    ap.add_argument("--threads", type=int, default=384)
+    ap.add_argument("--ctas-per-sm", type=int, default=2)
+    ap.add_argument("--unroll", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=400)
+    args = ap.parse_args()
+    h = capi.Handle(0)
+    n_mol = args.n_mol
+    base, systems = make(h, n_mol, 8)
+    p = capi.Params.make(0.01, 1e-3)
+    dof = 3.0 * n_mol - 3
+    a = capi.BussiArgs(synth.KT_100K, synth.TAU_5PS, synth.DT_1FS, dof, 0.1, (dof - 1) / 2)
+    st = capi.Stream()
+    G = min(148 * args.ctas_per_sm, (base.N + args.threads - 1) // args.threads)
+    # bitwise comparison on two fresh copies of the same system
+    out = {}
+    for variant in (1, 2):
+        h.set_tuning(variant=variant, threads=args.threads, ctas_per_sm=args.ctas_per_sm, unroll=args.unroll, stamps=0)
+        d = systems[variant]
+        call(h, "step", d, base, n_mol, p, a, st.ptr)
+        out[variant] = (d["force"].numpy(st.ptr).copy(), d["vel"].numpy(st.ptr).copy(), h.force_read(st.ptr), h.bussi_read(st.ptr))
+    same_f = np.array_equal(out[1][0], out[2][0])
+    same_v = np.array_equal(out[1][1], out[2][1])
+    print("variant 2 vs 1: force bitwise", same_f, " vel bitwise", same_v, " energies", out[1][2][0], out[2][2][0],
+          " alpha", out[1][3]["alpha"], out[2][3]["alpha"])
+    for variant in (1, 2):
+        h.set_tuning(variant=variant, stamps=0)
+        for k in range(10):
+            call(h, "step", systems[k % 8], base, n_mol, p, a, st.ptr)
+        capi.sync()
+        e0, e1 = capi.Event(), capi.Event()
+        e0.record(st.ptr)
+        for k in range(args.steps):
+            call(h, "step", systems[k % 8], base, n_mol, p, a, st.ptr)
+        e1.record(st.ptr)
+        us = e1.elapsed_ms_since(e0) / args.steps * 1e3
+        print(f"variant {variant}: {us:.2f} us/step back to back  frac {148 * base.N / (us * 1e-6) / 6454.9e9:.3f}")
+    h.set_tuning(variant=2, stamps=1)
+    for k in range(5):
+        call(h, "step", systems[k % 8], base, n_mol, p, a, st.ptr)
+    capi.sync()
+    print("launch | event | dip-reduce med/max | KE-reduce med/max | Dq wait+combine med/max | forces med/max | alpha wait+combine med/max | rescale med/max | span")
+    for k in range(6):
+        e0, e1 = capi.Event(), capi.Event()
+        e0.record(st.ptr)
+        call(h, "step", systems[(5 + k) % 8], base, n_mol, p, a, st.ptr)
+        e1.record(st.ptr)
+        ev = e1.elapsed_ms_since(e0) * 1e3
+        s = h.debug_stamps(G).astype(np.float64)[:, :7] * 1e-3
+        t0 = s[:, 0].min()
+        ph = [s[:, i + 1] - s[:, i] for i in range(6)]
+        print(f"{k:6d} | {ev:6.2f} | " + " | ".join(f"{np.median(x):6.2f} {x.max():6.2f}" for x in ph) + f" | {s[:, 6].max() - t0:6.2f}")
+
+
+if __name__ == "__main__":
+    main()
