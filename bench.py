@@ -185,6 +185,20 @@ def run_reference(args):
     return 0
 
 
+def ncu_traffic(n_mol):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the step kernel, per launch, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json; a number measured under the profiler, so it is
+    read from the committed summary, never taken live).  None when the capture is for another size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            t = json.load(fh)
+        if int(t.get("n_mol", -1)) != int(n_mol):
+            return None, None
+        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"]), t.get("source")
+    except Exception:
+        return None, None
+
+
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
@@ -349,6 +363,7 @@ def run_b200(args):
     # breaks the programmatic-dependent-launch overlap) is reported next to it as "isolated"
     t_launch = ms_fused / args.steps
     achieved = STEP_BYTES * N / (t_launch * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(n_mol)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_fused / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -357,13 +372,13 @@ def run_b200(args):
             "workload": f"synthetic {n_mol}-particle charged box + 1 photon, CavityForce g=1e-3 omegac=0.01 + "
                         f"BussiReservoir kT=100K tau=5ps (BASELINE configs[1])" + (
                             f"; {world} independent replicas, one per GPU (configs[2])" if world > 1 else ""),
-            "path": "cavb200_step: cavity force + Bussi thermostat in one launch, device-resident arrays",
+            "path": "cavb200_step: cavity force + Bussi thermostat in one launch (split-phase kernel), device-resident arrays",
             "l2": f"inputs larger than L2: rotating over {len(systems)} systems x {116 * N / 1e6:.0f} MB",
             "tuning": {k: h.get_tuning(k) for k in ("variant", "threads", "ctas_per_sm", "unroll", "pdl")},
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "k_fused<force,bussi> (cavb200_step)",
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_split (cavb200_step)",
             "algorithmic_bytes_per_particle": STEP_BYTES, "kernel_ms": t_launch, "peak_source": peak_src,
             "isolated": {"kernel_ms": t_step, "achieved": STEP_BYTES * N / (t_step * 1e-3) / 1e9,
                          "frac": STEP_BYTES * N / (t_step * 1e-3) / 1e9 / peak,

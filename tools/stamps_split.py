@@ -35,10 +35,13 @@ def main():
         d = systems[variant]
         call(h, "step", d, base, n_mol, p, a, st.ptr)
         out[variant] = (d["force"].numpy(st.ptr).copy(), d["vel"].numpy(st.ptr).copy(), h.force_read(st.ptr), h.bussi_read(st.ptr))
-    same_f = np.array_equal(out[1][0], out[2][0])
-    same_v = np.array_equal(out[1][1], out[2][1])
-    print("variant 2 vs 1: force bitwise", same_f, " vel bitwise", same_v, " energies", out[1][2][0], out[2][2][0],
-          " alpha", out[1][3]["alpha"], out[2][3]["alpha"])
+    for v in (2,):
+        same_f = np.array_equal(out[1][0], out[v][0])
+        same_v = np.array_equal(out[1][1], out[v][1])
+        relf = np.abs(out[1][0] - out[v][0]).max() / np.abs(out[1][0]).max()
+        relv = np.abs(out[1][1] - out[v][1]).max() / np.abs(out[1][1]).max()
+        print(f"variant {v} vs 1: force bitwise {same_f} (max rel {relf:.2e})  vel bitwise {same_v} (max rel {relv:.2e})  energies",
+              out[1][2][0], out[v][2][0], " alpha", out[1][3]["alpha"], out[v][3]["alpha"])
     for variant in (1, 2):
         h.set_tuning(variant=variant, stamps=0)
         for k in range(10):
@@ -51,22 +54,27 @@ def main():
         e1.record(st.ptr)
         us = e1.elapsed_ms_since(e0) / args.steps * 1e3
         print(f"variant {variant}: {us:.2f} us/step back to back  frac {148 * base.N / (us * 1e-6) / 6454.9e9:.3f}")
-    h.set_tuning(variant=2, stamps=1)
-    for k in range(5):
-        call(h, "step", systems[k % 8], base, n_mol, p, a, st.ptr)
-    capi.sync()
-    print("launch | event | dip-reduce med/max | KE-reduce med/max | Dq wait+combine med/max | forces med/max | alpha wait+combine med/max | rescale med/max | span")
-    for k in range(6):
-        e0, e1 = capi.Event(), capi.Event()
-        e0.record(st.ptr)
-        call(h, "step", systems[(5 + k) % 8], base, n_mol, p, a, st.ptr)
-        e1.record(st.ptr)
-        ev = e1.elapsed_ms_since(e0) * 1e3
-        s = h.debug_stamps(G).astype(np.float64)[:, :7] * 1e-3
-        t0 = s[:, 0].min()
-        ph = [s[:, i + 1] - s[:, i] for i in range(6)]
-        print(f"{k:6d} | {ev:6.2f} | " + " | ".join(f"{np.median(x):6.2f} {x.max():6.2f}" for x in ph) + f" | {s[:, 6].max() - t0:6.2f}")
-
+    for variant in (2,):
+        h.set_tuning(variant=variant, stamps=1)
+        print("variant", variant, "(2: dip-R | KE-R | Dq combine | forces | alpha combine | rescale;  "
+              "3: dip-R | KE-R / helper merge | sync | forces / helper merge | sync | rescale;  4: dip-R | KE-R | [s2->s3 n/a] | forces | [n/a] | [n/a])  med max per phase, span")
+        for k in range(5):
+            call(h, "step", systems[k % 8], base, n_mol, p, a, st.ptr)
+        capi.sync()
+        for k in range(6):
+            e0, e1 = capi.Event(), capi.Event()
+            e0.record(st.ptr)
+            call(h, "step", systems[(5 + k) % 8], base, n_mol, p, a, st.ptr)
+            e1.record(st.ptr)
+            ev = e1.elapsed_ms_since(e0) * 1e3
+            s = h.debug_stamps(G).astype(np.float64)[:, :7] * 1e-3
+            t0 = s[:, 0].min()
+            ph = [s[:, i + 1] - s[:, i] for i in range(6)]
+            print(f"{k:6d} | {ev:6.2f} | " + " | ".join(f"{np.median(x):6.2f} {x.max():6.2f}" for x in ph) + f" | {s[:, 6].max() - t0:6.2f}")
+            if variant == 4:
+                rel = s - t0
+                names = ["start", "dipR+pub", "KE pub", "F: Dq ready", "F: forces done", "K: alpha ready", "end"]
+                print("        since first start, med/max: " + "  ".join(f"{n} {np.median(rel[:, i]):.2f}/{rel[:, i].max():.2f}" for i, n in enumerate(names)))
 
 if __name__ == "__main__":
     main()
