@@ -61,6 +61,8 @@ def measured_peak():
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread of this process
+    (a sample every ~2 ms); nvidia-smi -lms as the fallback when pynvml is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -68,27 +70,83 @@ class ClockSampler:
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.samples = []  # (sm_mhz, reasons bitmask)
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except (ValueError, IndexError):
+                pass
+        return self.gpu
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ["nvidia-smi", "-i", str(self._visible_index()), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM))
+                try:
+                    rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
+                except Exception:
+                    rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+                self.samples.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Number of samples so far (to report how many fell inside a region)."""
+        return len(self.samples) if self.nvml else len(self.rows)
+
+    def stop(self, first=0, last=None):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            n = self.nvml
+            bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+            sel = self.samples[first:last] or self.samples
+            sm = [x[0] for x in sel]
+            reasons = sorted(k for k, b in bits.items() if any(x[1] & b for x in sel))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, sampled during the timed regions"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             parts = [x.strip() for x in r.split(",")]
             if len(parts) < 6:
@@ -102,7 +160,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -296,7 +354,8 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.1)  # let nvidia-smi start before the timed region
+        time.sleep(0.05)
+    m0 = sampler.mark()
     ms_fused, launches_fused = timed(True, args.steps, args.warmup)
     ms_sep, launches = timed(False, args.steps, args.warmup + args.steps)
 
@@ -323,7 +382,7 @@ def run_b200(args):
     capi.sync()
     t_force = float(np.mean([b.elapsed_ms_since(a) for a, b, c in evs]))
     t_bussi = float(np.mean([c.elapsed_ms_since(b) for a, b, c in evs]))
-    clocks = sampler.stop() if rank == 0 else None  # sampled from before the timed regions to here
+    clocks = sampler.stop(first=m0) if rank == 0 else None  # samples from the start of the first timed region to here
 
     # e2e: host-buffer C-ABI call, pinned host arrays, copies inside the timed region
     e2e_steps = max(3, min(args.steps, 20))
@@ -408,7 +467,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-mol", type=int, default=1_000_000)

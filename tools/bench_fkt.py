@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""tools/bench_fkt.py -- BASELINE configs[4]: F(k,t) on a 1M-particle trajectory, 64 wave vectors, 1000
+time origins.  rho[t][k] = sum_j exp(i k.r_j(t)) for a batch of T frames per launch (frames are
+generated on the host as a random walk and rotated so the timed input is larger than L2), then
+F[o][l] for all origins/lags.  Reports (particle, k) sincos pairs/s, the time 1000 origins take, the
+GB/s of position traffic, and the NumPy restatement of the reference (oracle) timed on a bounded sample.
+
+    python tools/bench_fkt.py [--n 1000000] [--K 64] [--frames 16] [--origins 1000]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cav_hoomd_b200 import capi, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--K", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=16, help="frames per launch")
+    ap.add_argument("--origins", type=int, default=1000)
+    ap.add_argument("--stride", type=int, default=4, choices=[3, 4])
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    N, K, T = args.n + 1, args.K, args.frames
+    h = capi.Handle(0)
+    if args.threads:
+        h.set_tuning(rhok_threads=args.threads)
+    s = synth.make_system(args.n)
+    rng = np.random.default_rng(7)
+    kvec = synth.fibonacci_sphere(K) * 1.0
+    d_k = capi.DeviceArray.from_numpy(kvec)
+    # T frames: random walk, sigma 0.05 Bohr, HOOMD Scalar4 layout or xyz
+    frames = np.empty((T, N, args.stride))
+    cur = s.pos.copy()
+    for t in range(T):
+        cur[:, :3] += 0.05 * rng.standard_normal((N, 3))
+        frames[t, :, :3] = cur[:, :3]
+        if args.stride == 4:
+            frames[t, :, 3] = cur[:, 3]
+    nbuf = max(2, int(400e6 // frames.nbytes) + 1)
+    d_frames = [capi.DeviceArray.from_numpy(frames) for _ in range(nbuf)]
+    d_rho = capi.DeviceArray((T, K, 2), np.float64)
+    st = capi.Stream()
+    for k in range(3):
+        h.rhok(d_frames[k % nbuf], args.stride, N * args.stride, N, T, d_k, K, d_rho, st.ptr)
+    capi.sync()
+    launches = max(4, min(40, args.origins // T))
+    e0, e1 = capi.Event(), capi.Event()
+    l0 = h.launch_count
+    e0.record(st.ptr)
+    for k in range(launches):
+        h.rhok(d_frames[k % nbuf], args.stride, N * args.stride, N, T, d_k, K, d_rho, st.ptr)
+    e1.record(st.ptr)
+    ms = e1.elapsed_ms_since(e0)
+    per_frame_ms = ms / (launches * T)
+    pairs_per_s = N * K / (per_frame_ms * 1e-3)
+    rho = d_rho.numpy(st.ptr)
+    # correlation over `origins` frames x `origins` lags of synthetic rho (tiny next to the field sum)
+    To = args.origins
+    big = np.tile(rho, (To // T + 1, 1, 1))[:To]
+    d_big = capi.DeviceArray.from_numpy(np.ascontiguousarray(big))
+    d_F = capi.DeviceArray((To, To), np.float64)
+    h.fkt(d_big, To, K, To, To, d_F, st.ptr)
+    capi.sync()
+    e0.record(st.ptr)
+    h.fkt(d_big, To, K, To, To, d_F, st.ptr)
+    e1.record(st.ptr)
+    ms_corr = e1.elapsed_ms_since(e0)
+    # check one frame against the NumPy restatement and time it (bounded sample)
+    out = {
+        "workload": f"F(k,t): N={N} particles, K={K} wave vectors, {T} frames per launch, stride {args.stride} doubles/particle",
+        "ms_per_frame": per_frame_ms, "sincos_pairs_per_s": pairs_per_s,
+        "seconds_for_origins": per_frame_ms * 1e-3 * args.origins + ms_corr * 1e-3, "origins": args.origins,
+        "position_GBs": N * 8 * args.stride / (per_frame_ms * 1e-3) / 1e9,
+        "ms_correlation_all_origins_x_lags": ms_corr, "gpu_launches": h.launch_count - l0,
+    }
+    if not args.no_cpu:
+        from oracle import oracle as O
+        n_s = min(N, 200_000)
+        t0 = time.perf_counter()
+        ref = O.numpy_density_field(frames[0, :n_s, :3], kvec)
+        dt = time.perf_counter() - t0
+        d_one = capi.DeviceArray.from_numpy(np.ascontiguousarray(frames[0, :n_s, :3]))
+        d_r1 = capi.DeviceArray((1, K, 2), np.float64)
+        h.rhok(d_one, 3, n_s * 3, n_s, 1, d_k, K, d_r1, st.ptr)
+        got = d_r1.numpy(st.ptr)[0]
+        err = np.abs((got[:, 0] + 1j * got[:, 1]) - ref).max() / np.abs(ref).max()
+        out["cpu_numpy"] = {"sincos_pairs_per_s": n_s * K / dt, "sample": f"{n_s} particles x {K} k, 1 frame, 1 thread",
+                            "max_rel_err_gpu_vs_numpy": float(err)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

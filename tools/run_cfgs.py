@@ -10,7 +10,7 @@ p = capi.Params.make(0.01, 1e-3)
 dof = 3.0 * n_mol - 3
 a = capi.BussiArgs(synth.KT_100K, synth.TAU_5PS, synth.DT_1FS, dof, 0.1, (dof - 1) / 2)
 st = capi.Stream()
-for variant, threads, ctas in ((2, 384, 2), (2, 768, 1), (2, 640, 1), (2, 512, 1), (2, 256, 2), (2, 320, 2), (2, 352, 2), (2, 384, 2)):
+for variant, threads, ctas in ((2, 384, 2),):
     h.set_tuning(variant=variant, threads=threads, ctas_per_sm=ctas, unroll=2)
     for kind, nb in (("step", 148),):
         for k in range(10):
