@@ -405,6 +405,31 @@ def run_b200(args):
         e2e_s = float(t.item())
     e2e_value = world * N * e2e_steps / e2e_s / 1e6
 
+    # raw PCIe rates of this box (pinned, 32 MB copies, one direction at a time and both together):
+    # the e2e step moves 84 B/particle in and 64 B/particle out, and no force byte can leave before
+    # the last position byte has arrived, so its floor is (84 B in + 32 B out) / PCIe rate
+    pcie = None
+    if rank == 0:
+        lib = capi.load()
+        nb = 32 * N
+        s2 = capi.Stream()
+        def rate(fn, reps=6):
+            fn()
+            capi.sync()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            capi.sync()
+            return nb * reps / (time.perf_counter() - t0) / 1e9
+        h2d = rate(lambda: lib.cavb200_memcpy_h2d(systems[0].pos.ptr, pin["pos"].ptr, nb, st))
+        d2h = rate(lambda: lib.cavb200_memcpy_d2h(pin_force.ptr, systems[0].force.ptr, nb, st))
+        def both():
+            lib.cavb200_memcpy_h2d(systems[0].pos.ptr, pin["pos"].ptr, nb, st)
+            lib.cavb200_memcpy_d2h(pin_force.ptr, systems[1].force.ptr, nb, s2.ptr)
+        duplex = 2 * rate(both)
+        floor_ms = (52 * N + 32 * n_mol) / (h2d * 1e6) + 32 * N / (d2h * 1e6)
+        pcie = {"h2d_GBs": h2d, "d2h_GBs": d2h, "duplex_GBs": duplex, "dependency_floor_ms_per_step": floor_ms}
+
     # sanity: the run must have produced finite forces and a sane alpha (not a timing of nothing)
     en, dip, ph = h.force_read(st)
     bo = h.bussi_read(st)
@@ -454,7 +479,7 @@ def run_b200(args):
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 52 * N + 32 * n_mol,
                 "d2h_bytes_per_step": 32 * N + 32 * n_mol + 160, "steps": e2e_steps,
-                "path": "cavb200_step_host, pinned host buffers"},
+                "path": "cavb200_step_host, pinned host buffers", "ms_per_step": 1e3 * e2e_s / e2e_steps, "pcie": pcie},
         "gpu_launches": launches_fused, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -19,6 +19,7 @@ namespace cavb
     {
 constexpr uint32_t NO_INDEX = 0xFFFFFFFFu;
 constexpr unsigned long long HANDOFF_TIMEOUT_NS = 50000000ull; // 50 ms: a co-resident grid hands off in microseconds
+constexpr unsigned long long PEER_TIMEOUT_NS = 2000000000ull;  // 2 s: peer ranks may start late
 constexpr int MAX_PARTIALS = 2048; // upper bound on the grid of a reduce pass
 
 // One reduce-pass record per CTA (and, in sharded mode, per rank): 160 bytes = five 32-byte sectors,
@@ -164,6 +165,15 @@ __device__ __forceinline__ double4 ld256_cg(const double4* p)
     {
     double4 r;
     asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+    }
+__device__ __forceinline__ double4 ld256_sys(const double4* p)
+    {
+    double4 r;
+    asm volatile("ld.relaxed.sys.global.v4.f64 {%0,%1,%2,%3}, [%4];"
                  : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
                  : "l"(p)
                  : "memory");

@@ -467,10 +467,13 @@ __device__ __forceinline__ void publish_record(Partial* dst, const Partial& src,
     }
 
 // Strong (L2) read of one sector; WAIT: poll until it carries this launch's epoch (bounded).
-template<bool WAIT>
+// SYS: the records are written by PEER GPUs over NVLink into this GPU's memory (sharded mode):
+// system-scope loads, and a timeout that tolerates ranks starting late.
+template<bool SYS> __device__ __forceinline__ double4 ld_rec(const double4* p) { return SYS ? ld256_sys(p) : ld256_cg(p); }
+template<bool WAIT, bool SYS = false>
 __device__ __forceinline__ double4 read_sector(const double4* p, unsigned long long epoch, bool& late)
     {
-    double4 s = ld256_cg(p);
+    double4 s = ld_rec<SYS>(p);
     if (WAIT)
         {
         if (!sector_ok(s, epoch))
@@ -479,8 +482,8 @@ __device__ __forceinline__ double4 read_sector(const double4* p, unsigned long l
             do
                 {
                 __nanosleep(64);
-                s = ld256_cg(p);
-                if (globaltimer_ns() - t0 > HANDOFF_TIMEOUT_NS) // never hang the GPU
+                s = ld_rec<SYS>(p);
+                if (globaltimer_ns() - t0 > (SYS ? PEER_TIMEOUT_NS : HANDOFF_TIMEOUT_NS)) // never hang the GPU
                     {
                     late = true;
                     break;
@@ -538,7 +541,7 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 //   * the vote for the first 'L' particle, the pair trees and the finalize need TWO block barriers;
 //   * the photon position (sector 3) is fetched by the one lane whose record holds the candidate,
 //     concurrently with the tree; sector 4 is touched only when several 'L' particles exist.
-template<bool FORCE, bool BUSSI, bool WAIT, bool FINALIZE>
+template<bool FORCE, bool BUSSI, bool WAIT, bool FINALIZE, bool SYS = false>
 __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, int G, unsigned long long epoch,
                                               const ForceIn& f, const BussiIn& b, BlockScratch& sc, Scalars* scalars,
                                               bool publish, unsigned long long* dbg = nullptr)
@@ -559,22 +562,22 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
             {
             const double4* p = reinterpret_cast<const double4*>(recs + j);
             // issue all sector reads before looking at any of them
-            double4 s2 = ld256_cg(p + 2), s0, s1;
+            double4 s2 = ld_rec<SYS>(p + 2), s0, s1;
             if (FORCE)
                 {
-                s0 = ld256_cg(p + 0);
-                s1 = ld256_cg(p + 1);
+                s0 = ld_rec<SYS>(p + 0);
+                s1 = ld_rec<SYS>(p + 1);
                 }
             if (WAIT)
                 {
                 if (!sector_ok(s2, epoch))
-                    s2 = read_sector<true>(p + 2, epoch, late);
+                    s2 = read_sector<true, SYS>(p + 2, epoch, late);
                 if (FORCE)
                     {
                     if (!sector_ok(s0, epoch))
-                        s0 = read_sector<true>(p + 0, epoch, late);
+                        s0 = read_sector<true, SYS>(p + 0, epoch, late);
                     if (!sector_ok(s1, epoch))
-                        s1 = read_sector<true>(p + 1, epoch, late);
+                        s1 = read_sector<true, SYS>(p + 1, epoch, late);
                     }
                 }
             if (FORCE)
@@ -610,9 +613,9 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
             const bool i_hold = (wmin != ~0ull) && (mykey == wmin);
             if (i_hold)
                 {
-                s3 = read_sector<WAIT>(reinterpret_cast<const double4*>(recs + myrec) + 3, epoch, late);
+                s3 = read_sector<WAIT, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 3, epoch, late);
                 if (!FINALIZE) // a rank-level merge may lose the global vote later: keep the term too
-                    s4 = read_sector<WAIT>(reinterpret_cast<const double4*>(recs + myrec) + 4, epoch, late);
+                    s4 = read_sector<WAIT, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 4, epoch, late);
                 }
             warp_tree<FORCE, BUSSI>(a);
             if (i_hold)
@@ -675,11 +678,11 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
                 for (int j = lane; j < G; j += 32)
                     {
                     const double4* p = reinterpret_cast<const double4*>(recs + j);
-                    const double4 s2 = read_sector<WAIT>(p + 2, epoch, late2);
+                    const double4 s2 = read_sector<WAIT, SYS>(p + 2, epoch, late2);
                     const unsigned long long key = dbits(s2.y);
                     if (key != ~0ull && (key & ~MULTI_L_BIT) != gmin)
                         {
-                        const double4 s4 = read_sector<WAIT>(p + 4, epoch, late2);
+                        const double4 s4 = read_sector<WAIT, SYS>(p + 4, epoch, late2);
                         two_sum_acc(extra.dhi[0], extra.dlo[0], s4.x);
                         two_sum_acc(extra.dhi[1], extra.dlo[1], s4.y);
                         two_sum_acc(extra.dhi[2], extra.dlo[2], s4.z);

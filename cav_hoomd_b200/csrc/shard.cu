@@ -34,6 +34,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     return v;
     }
 
+// mailbox of a rank: [kind: 0 two-kernel path / split dipole, 1 split KE][parity][16 ranks] records
+constexpr int MAILBOX_RECORDS = 64;
+constexpr unsigned long long SHARD_EPOCH_TAG = 1ull << 62; // keeps shard epochs apart from the single-GPU counter
+
 struct PeerTable
     {
     Partial* mailbox[16];
@@ -42,7 +46,7 @@ struct PeerTable
 
 // kernel A
 template<int UNROLL, int LB>
-__global__ void __launch_bounds__(LB, 1)
+__global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_shard_reduce(ForceIn f, BussiIn b, Partial* recs, unsigned long long* ticket, Partial* rank_record, int mode,
                    int rank, int nranks, unsigned long long seq, PeerTable peers)
     {
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(LB, 1)
 
 // kernel B
 template<int UNROLL, int LB>
-__global__ void __launch_bounds__(LB, 1)
+__global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_shard_apply(ForceIn f, BussiIn b, const Partial* gathered, Scalars* scalars, int mode, int nranks,
                   unsigned long long seq, const unsigned long long* my_flags)
     {
@@ -114,6 +118,57 @@ __global__ void __launch_bounds__(LB, 1)
     if (sc.fin.timeout)
         return;
     apply_phase<true, true, UNROLL>(sc.fin, f, b);
+    }
+
+// ---- ONE kernel per rank and step (mode 1, default) ----------------------------------------------
+// The split-phase schedule of k_split with the NVLink exchange inside it:
+//   dipole reduce -> CTA records -> CTA 0 folds them into the rank's record and stores it straight
+//   into every peer's mailbox (peer memory, one 32-byte sector per store, self-validating with the
+//   step number -- no flag, no fence, no collective call, no second launch);
+//   KE reduce -> the same for the kinetic energy;
+//   every CTA then folds the nranks dipole records that arrived in ITS OWN GPU's mailbox (rank order,
+//   so every CTA of every rank forms bit-identical Dq) and writes forces; the KE records have crossed
+//   NVLink in the meantime: alpha, rescale.
+// Each exchange therefore has a whole streaming pass to complete behind.
+template<int UNROLL, int LB>
+__global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
+    k_shard_split(ForceIn f, BussiIn b, Partial* recsF, Partial* recsB, Scalars* scalars, const Partial* my_mailbox,
+                  int rank, int nranks, unsigned long long seq, PeerTable peers)
+    {
+    __shared__ BlockScratch sc;
+    const unsigned long long epoch = seq | SHARD_EPOCH_TAG;
+    const size_t slot = (size_t)(seq & 1ull) * 16;
+    if (threadIdx.x == 0)
+        sc.flags = 0u;
+    reduce_phase<true, false, UNROLL>(f, b, sc);
+    if (threadIdx.x == 0)
+        publish_record(recsF + blockIdx.x, sc.rec, epoch);
+    if (blockIdx.x == 0)
+        {
+        combine_phase<true, false, true, false>(recsF, (int)gridDim.x, epoch, f, b, sc, nullptr, false);
+        if ((int)threadIdx.x < nranks)
+            publish_record(peers.mailbox[threadIdx.x] + slot + rank, sc.rec, epoch);
+        __syncthreads(); // sc.rec is rewritten by the next block merge
+        }
+    reduce_phase<false, true, UNROLL>(f, b, sc);
+    if (threadIdx.x == 0)
+        publish_record(recsB + blockIdx.x, sc.rec, epoch);
+    if (blockIdx.x == 0)
+        {
+        combine_phase<false, true, true, false>(recsB, (int)gridDim.x, epoch, f, b, sc, nullptr, false);
+        if ((int)threadIdx.x < nranks)
+            publish_record(peers.mailbox[threadIdx.x] + 32 + slot + rank, sc.rec, epoch);
+        __syncthreads();
+        }
+    combine_phase<true, false, true, true, true>(my_mailbox + slot, nranks, epoch, f, b, sc, scalars, blockIdx.x == 0);
+    const bool timeout_f = sc.fin.timeout != 0;
+    if (!timeout_f)
+        apply_phase<true, false, UNROLL>(sc.fin, f, b);
+    __syncthreads();
+    combine_phase<false, true, true, true, true>(my_mailbox + 32 + slot, nranks, epoch, f, b, sc, scalars, blockIdx.x == 0);
+    if (sc.fin.timeout || timeout_f)
+        return;
+    apply_phase<false, true, UNROLL>(sc.fin, f, b);
     }
 
 // ---- NCCL through dlopen ----------------------------------------------------------------------
@@ -155,11 +210,11 @@ static int ensure_mailbox(cavb200_handle* h)
     if (sh.mailbox_alloc)
         return 0;
     // [2 parities][16 ranks] records + [16] flags, zeroed
-    const size_t bytes = sizeof(Partial) * 32 + sizeof(unsigned long long) * 16;
+    const size_t bytes = sizeof(Partial) * MAILBOX_RECORDS + sizeof(unsigned long long) * 16;
     CAVB_CHECK(cudaMalloc(&sh.mailbox_alloc, bytes));
     CAVB_CHECK(cudaMemset(sh.mailbox_alloc, 0, bytes));
     sh.gather = reinterpret_cast<Partial*>(sh.mailbox_alloc);
-    sh.flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(sh.mailbox_alloc) + sizeof(Partial) * 32);
+    sh.flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(sh.mailbox_alloc) + sizeof(Partial) * MAILBOX_RECORDS);
     sh.peer_mailbox[0] = sh.gather;
     sh.peer_flags[0] = sh.flags;
     return 0;
@@ -194,6 +249,24 @@ template<int UNROLL, int LB> static int launch_shard_t(cavb200_handle* h, const 
         peers.mailbox[0] = sh.gather;
         peers.flags[0] = sh.flags;
         }
+    if (mode == 1 && h->tune.variant >= 1 && b.rescale)
+        {
+        // single persistent kernel: the CTAs wait on each other's records, so the grid must be co-resident
+        int per_sm = 0;
+        CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shard_split<UNROLL, LB>, threads, 0));
+        if (per_sm < 1)
+            return (int)cudaErrorLaunchOutOfResources;
+        int g = grid;
+        if (g > per_sm * h->num_sms)
+            g = per_sm * h->num_sms;
+        if (g > MAX_PARTIALS / 2)
+            g = MAX_PARTIALS / 2;
+        k_shard_split<UNROLL, LB><<<g, threads, 0, s>>>(f, b, h->partials, h->partials + MAX_PARTIALS / 2, h->scalars,
+                                                        sh.gather, sh.rank, nranks, sh.seq, peers);
+        CAVB_CHECK(cudaGetLastError());
+        h->launches += 1;
+        return 0;
+        }
     Partial* rank_record = h->partials + MAX_PARTIALS - 1;
     k_shard_reduce<UNROLL, LB><<<grid, threads, 0, s>>>(f, b, h->partials, h->counters + 4, rank_record, mode, sh.rank, nranks,
                                                      sh.seq, peers);
@@ -221,6 +294,8 @@ int launch_shard_step(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cud
     case 4:
         return launch_shard_t<4, 512>(h, *f, *b, s);
     default:
+        if (h->tune.threads <= 384)
+            return launch_shard_t<2, 384>(h, *f, *b, s);
         return launch_shard_t<2, 1024>(h, *f, *b, s);
         }
     }
@@ -320,7 +395,7 @@ int cavb200_shard_mailbox_open(cavb200_handle* h, const void* handles, int rank,
             CAVB_CHECK(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
             }
         sh.peer_mailbox[r] = reinterpret_cast<Partial*>(base);
-        sh.peer_flags[r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + sizeof(Partial) * 32);
+        sh.peer_flags[r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + sizeof(Partial) * MAILBOX_RECORDS);
         }
     sh.rank = rank;
     sh.nranks = nranks;
