@@ -15,28 +15,98 @@
 
 namespace cavb
     {
+#ifndef RHOK_MIN_CTAS
+#define RHOK_MIN_CTAS 2
+#endif
 constexpr int RHOK_TILE = 1024; // particles per shared-memory tile (24 KB)
 
-__global__ void __launch_bounds__(1024)
+// sin and cos of one argument, |x| < 2^20, both to < 1 ulp-ish (abs. error ~2e-16).
+// The library sincos() costs ~70 issue slots per call here, two thirds of them integer/selection/slow-path
+// plumbing, and `ncu` showed the first kernel issue-bound (88 % issue slots busy, FP64 pipe at 50 %,
+// profiles/ncu_rhok_r1a_summary.txt).  This one is 21 FP64 instructions and ~8 integer ones:
+//   n = rint(x * 2/pi) by the 1.5*2^52 trick;  r = x - n*pio2_hi - n*pio2_lo with two FMAs (n*pio2_hi is
+//   exact inside the FMA for |n| < 2^20);  fdlibm's __kernel_sin/__kernel_cos minimax polynomials on
+//   [-pi/4, pi/4] (public-domain constants, < 1 ulp);  quadrant fix-up by swapping and flipping sign bits.
+// (the constants sit in constant memory so that every DFMA takes its coefficient as a c[bank][offset]
+// operand; as literals the compiler rebuilt each one with two UMOVs inside the loop -- 25 extra issue
+// slots per pair)
+__constant__ double SC[18] = {
+    6755399441055744.0,          // 0  1.5 * 2^52
+    6.36619772367581382433e-01,  // 1  2/pi
+    1.57079632679489655800e+00,  // 2  pi/2 hi
+    6.12323399573676603587e-17,  // 3  pi/2 lo
+    1.58969099521155010221e-10,  // 4  S6
+    -2.50507602534068634195e-08, // 5  S5
+    2.75573137070700676789e-06,  // 6  S4
+    -1.98412698298579493134e-04, // 7  S3
+    8.33333333332248946124e-03,  // 8  S2
+    -1.66666666666666324348e-01, // 9  S1
+    -1.13596475577881948265e-11, // 10 C6
+    2.08757232129817482790e-09,  // 11 C5
+    -2.75573143513906633035e-07, // 12 C4
+    2.48015872894767294178e-05,  // 13 C3
+    -1.38888888888741095749e-03, // 14 C2
+    4.16666666666666019037e-02,  // 15 C1
+    -0.5, 1.0};
+__device__ __forceinline__ void sincos_lean(double x, double& s, double& c)
+    {
+    const double t = __fma_rn(x, SC[1], SC[0]);
+    const int q = __double2loint(t);
+    const double n = __dadd_rn(t, -SC[0]);
+    double r = __fma_rn(-n, SC[2], x);
+    r = __fma_rn(-n, SC[3], r);
+    const double z = __dmul_rn(r, r);
+    double ps = __fma_rn(z, SC[4], SC[5]);
+    ps = __fma_rn(z, ps, SC[6]);
+    ps = __fma_rn(z, ps, SC[7]);
+    ps = __fma_rn(z, ps, SC[8]);
+    ps = __fma_rn(z, ps, SC[9]);
+    const double sr = __fma_rn(__dmul_rn(r, z), ps, r);
+    double pc = __fma_rn(z, SC[10], SC[11]);
+    pc = __fma_rn(z, pc, SC[12]);
+    pc = __fma_rn(z, pc, SC[13]);
+    pc = __fma_rn(z, pc, SC[14]);
+    pc = __fma_rn(z, pc, SC[15]);
+    const double cr = __fma_rn(__dmul_rn(z, z), pc, __fma_rn(z, SC[16], SC[17]));
+    // quadrant q & 3:  0: (s, c) = (sr, cr)   1: (cr, -sr)   2: (-sr, -cr)   3: (-cr, sr)
+    const bool odd = q & 1;
+    const double ss = odd ? cr : sr;
+    const double cc = odd ? sr : cr;
+    const int fs = (q & 2) << 30;       // sign flip of sin in quadrants 2, 3
+    const int fc = ((q + 1) & 2) << 30; // sign flip of cos in quadrants 1, 2
+    s = __hiloint2double(__double2hiint(ss) ^ fs, __double2loint(ss));
+    c = __hiloint2double(__double2hiint(cc) ^ fc, __double2loint(cc));
+    }
+
+// grid (P, T); thread (pg, kq): particle group pg walks the tile with stride `groups`, kq owns KB
+// consecutive wave vectors whose components and (re, im) accumulators live in registers, so the three
+// shared-memory loads and the loop bookkeeping of a particle are paid once per KB (particle, k) pairs.
+template<int KB>
+__global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
     k_rhok(const double* __restrict__ pos, uint32_t stride, unsigned long long frame_stride, uint32_t N,
-           const double* __restrict__ kvec, uint32_t k0, uint32_t KS, uint32_t K, double* __restrict__ out,
-           uint32_t P, int direct)
+           const double* __restrict__ kvec, uint32_t k0, uint32_t Ks, uint32_t K, double* __restrict__ out, uint32_t P,
+           int direct)
     {
     __shared__ double sx[RHOK_TILE], sy[RHOK_TILE], sz[RHOK_TILE];
-    extern __shared__ double sred[]; // [groups][KS][2]
+    extern __shared__ double sred[]; // [groups][KQ * KB][2]
 
     const uint32_t t = blockIdx.y, p = blockIdx.x;
     const uint32_t tid = threadIdx.x;
-    const uint32_t groups = blockDim.x / KS;
-    const uint32_t kslot = tid % KS, group = tid / KS;
-    const bool active = group < groups;
+    const uint32_t KQ = (Ks + KB - 1) / KB;      // k-quads of this slab (host guarantees KQ <= blockDim.x)
+    const uint32_t groups = blockDim.x / KQ;
+    const uint32_t kq = tid % KQ, pg = tid / KQ;
+    const bool active = pg < groups;
 
-    double kx = 0, ky = 0, kz = 0;
-    if (active)
+    double kx[KB], ky[KB], kz[KB], re[KB], im[KB];
+#pragma unroll
+    for (int m = 0; m < KB; m++)
         {
-        kx = __ldg(kvec + 3 * (k0 + kslot) + 0);
-        ky = __ldg(kvec + 3 * (k0 + kslot) + 1);
-        kz = __ldg(kvec + 3 * (k0 + kslot) + 2);
+        const uint32_t k = kq * KB + m;
+        const bool in = active && k < Ks;
+        kx[m] = in ? __ldg(kvec + 3 * (k0 + k) + 0) : 0.0;
+        ky[m] = in ? __ldg(kvec + 3 * (k0 + k) + 1) : 0.0;
+        kz[m] = in ? __ldg(kvec + 3 * (k0 + k) + 2) : 0.0;
+        re[m] = im[m] = 0.0;
         }
 
     // contiguous slice of this frame, in whole tiles
@@ -46,7 +116,6 @@ __global__ void __launch_bounds__(1024)
     const uint32_t tile_hi = min(tiles, tile_lo + tiles_per);
     const double* frame = pos + (unsigned long long)t * frame_stride;
 
-    double re = 0.0, im = 0.0;
     for (uint32_t tile = tile_lo; tile < tile_hi; tile++)
         {
         const uint32_t base = tile * RHOK_TILE;
@@ -76,55 +145,99 @@ __global__ void __launch_bounds__(1024)
         __syncthreads();
         if (active)
             {
-            for (uint32_t j = group; j < n; j += groups)
+            for (uint32_t j = pg; j < n; j += groups)
                 {
-                // analysis.py:42 np.dot(positions, k_vec): x kx + y ky + z kz
-                const double kr = __dadd_rn(__dadd_rn(__dmul_rn(sx[j], kx), __dmul_rn(sy[j], ky)), __dmul_rn(sz[j], kz));
-                double s, c;
-                sincos(kr, &s, &c);
-                re += c;
-                im += s;
+                const double x = sx[j], y = sy[j], z = sz[j];
+                double kr[KB];
+                bool huge = false;
+#pragma unroll
+                for (int m = 0; m < KB; m++)
+                    {
+                    // analysis.py:42 np.dot(positions, k_vec) = x kx + y ky + z kz (NumPy hands this to a BLAS
+                    // gemv, which contracts to FMAs on any AVX2 host; so does this)
+                    kr[m] = __fma_rn(z, kz[m], __fma_rn(y, ky[m], __dmul_rn(x, kx[m])));
+                    // |kr| >= 2^20, inf or nan: exponent test on the integer pipe (DSETP would sit on the FP64 pipe)
+                    huge = huge || (__double2hiint(kr[m]) & 0x7fffffff) >= 0x41300000;
+                    }
+                if (!huge)
+                    {
+                    // one basic block for the KB independent chains: coefficients are fetched once
+#pragma unroll
+                    for (int m = 0; m < KB; m++)
+                        {
+                        double sn, cs;
+                        sincos_lean(kr[m], sn, cs);
+                        re[m] += cs;
+                        im[m] += sn;
+                        }
+                    }
+                else
+                    {
+                    for (int m = 0; m < KB; m++)
+                        {
+                        double sn, cs;
+                        sincos(kr[m], &sn, &cs); // huge arguments (and inf/nan): the library's Payne-Hanek path
+                        re[m] += cs;
+                        im[m] += sn;
+                        }
+                    }
                 }
             }
         }
 
-    // fold the groups (fixed order)
+    // fold the particle groups (fixed order)
+    const uint32_t KP = KQ * KB;
     if (active)
         {
-        sred[(group * KS + kslot) * 2 + 0] = re;
-        sred[(group * KS + kslot) * 2 + 1] = im;
+#pragma unroll
+        for (int m = 0; m < KB; m++)
+            {
+            sred[(pg * KP + kq * KB + m) * 2 + 0] = re[m];
+            sred[(pg * KP + kq * KB + m) * 2 + 1] = im[m];
+            }
         }
     __syncthreads();
-    if (tid < KS)
+    for (uint32_t k = tid; k < Ks; k += blockDim.x)
         {
         double r = 0.0, i = 0.0;
         for (uint32_t g = 0; g < groups; g++)
             {
-            r += sred[(g * KS + tid) * 2 + 0];
-            i += sred[(g * KS + tid) * 2 + 1];
+            r += sred[(g * KP + k) * 2 + 0];
+            i += sred[(g * KP + k) * 2 + 1];
             }
-        double* dst = direct ? out + ((unsigned long long)t * K + k0 + tid) * 2
-                             : out + (((unsigned long long)t * P + p) * K + k0 + tid) * 2;
+        double* dst = direct ? out + ((unsigned long long)t * K + k0 + k) * 2
+                             : out + (((unsigned long long)t * P + p) * K + k0 + k) * 2;
         dst[0] = r;
         dst[1] = i;
         }
     }
 
+// one warp per (t, k): lane L adds slices L, L + 32, ... (independent loads), then a fixed shuffle tree
 __global__ void k_rhok_fold(const double* __restrict__ part, uint32_t P, uint32_t K, uint32_t T, double* __restrict__ rho)
     {
-    const unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; // (t, k) pair
+    const unsigned long long e = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // (t, k) pair
+    const uint32_t lane = threadIdx.x & 31;
     if (e >= (unsigned long long)T * K)
         return;
     const unsigned long long t = e / K, k = e % K;
     double r = 0.0, i = 0.0;
-    for (uint32_t p = 0; p < P; p++)
+    for (uint32_t p = lane; p < P; p += 32)
         {
-        const double* src = part + ((t * P + p) * K + k) * 2;
-        r += src[0];
-        i += src[1];
+        const double2 v = *reinterpret_cast<const double2*>(part + ((t * P + p) * K + k) * 2);
+        r += v.x;
+        i += v.y;
         }
-    rho[e * 2 + 0] = r;
-    rho[e * 2 + 1] = i;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1)
+        {
+        r += __shfl_xor_sync(0xffffffffu, r, m);
+        i += __shfl_xor_sync(0xffffffffu, i, m);
+        }
+    if (lane == 0)
+        {
+        rho[e * 2 + 0] = r;
+        rho[e * 2 + 1] = i;
+        }
     }
 
 // F[o][l] = mean_k Re(rho[o][k] conj(rho[o+l][k]))  (analysis.py:361: np.mean(np.real(f0 * np.conj(ft))))
@@ -171,9 +284,9 @@ extern "C" int cavb200_rhok(cavb200_handle* h, const double* pos, uint32_t strid
         CAVB_CHECK(cudaMemsetAsync(rho, 0, sizeof(double) * 2ull * K * T, s));
         return 0;
         }
-    const int threads = h->tune.rhok_threads;
+    const int threads = 256;
     const uint32_t tiles = (N + RHOK_TILE - 1) / RHOK_TILE;
-    uint32_t P = (32u * (uint32_t)h->num_sms + T - 1) / T;
+    uint32_t P = (24u * (uint32_t)h->num_sms + T - 1) / T;
     if (P > tiles)
         P = tiles;
     if (P < 1)
@@ -195,19 +308,22 @@ extern "C" int cavb200_rhok(cavb200_handle* h, const double* pos, uint32_t strid
             }
         target = h->rhok_partials;
         }
-    for (uint32_t k0 = 0; k0 < K; k0 += (uint32_t)threads)
+    // wave vectors in slabs of at most threads*KB = 1024 (one launch for the usual K); KB = 4 k per thread
+    constexpr int KB = 4;
+    for (uint32_t k0 = 0; k0 < K; k0 += (uint32_t)threads * KB)
         {
-        const uint32_t KS = (K - k0) < (uint32_t)threads ? (K - k0) : (uint32_t)threads;
-        const uint32_t groups = (uint32_t)threads / KS;
-        const size_t smem = sizeof(double) * 2 * groups * KS;
-        k_rhok<<<dim3(P, T), threads, smem, s>>>(pos, stride, frame_stride, N, kvec, k0, KS, K, target, P, direct);
+        const uint32_t Ks = (K - k0) < (uint32_t)threads * KB ? (K - k0) : (uint32_t)threads * KB;
+        const uint32_t KQ = (Ks + KB - 1) / KB;
+        const uint32_t groups = (uint32_t)threads / KQ;
+        const size_t smem = sizeof(double) * 2 * groups * KQ * KB;
+        k_rhok<KB><<<dim3(P, T), threads, smem, s>>>(pos, stride, frame_stride, N, kvec, k0, Ks, K, target, P, direct);
         CAVB_CHECK(cudaGetLastError());
         h->launches += 1;
         }
     if (!direct)
         {
         const unsigned long long pairs = (unsigned long long)T * K;
-        k_rhok_fold<<<(unsigned int)((pairs + 255) / 256), 256, 0, s>>>(target, P, K, T, rho);
+        k_rhok_fold<<<(unsigned int)((pairs * 32 + 255) / 256), 256, 0, s>>>(target, P, K, T, rho);
         CAVB_CHECK(cudaGetLastError());
         h->launches += 1;
         }
