@@ -122,7 +122,7 @@ def test_bussi_edge_cases(handle):
     assert handle.bussi_read()["alpha"] < 0
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("n_mol", [1000, 262145])
 def test_fused_step_equals_separate_calls(handle, coracle, n_mol, variant):
     """cavb200_step == cavb200_force followed by cavb200_bussi, and both == oracle."""
@@ -157,16 +157,17 @@ def test_fused_step_equals_separate_calls(handle, coracle, n_mol, variant):
     assert np.allclose(v_fused, vref, rtol=1e-12, atol=0)
 
 
-def test_step_under_cuda_graph(handle, coracle):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_step_under_cuda_graph(handle, coracle, variant):
     """The step captured in a CUDA graph and replayed gives the same result as direct launches
-    (the grid barrier keeps no host-side state)."""
+    (the hand-off keeps no host-side state)."""
     s = synth.make_system(50000)
     p = capi.Params.make(0.01, 1e-3)
     a = bargs(3.0 * 50000 - 3.0)
     dev = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
     d_f = capi.DeviceArray((s.N, 4), np.float64)
     st = capi.Stream()
-    handle.set_tuning(variant=1)
+    handle.set_tuning(variant=variant, threads=384, ctas_per_sm=2, unroll=2)
     handle.bussi_reset(st.ptr)
     g = handle.graph_capture(st.ptr, lambda: handle.step(dev["pos"], dev["charge"], dev["image"], d_f, dev["vel"], s.N,
                                                          s.box, s.L_typeid, p, 0, 50000, a, st.ptr))

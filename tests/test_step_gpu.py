@@ -1,0 +1,141 @@
+"""GPU parity of cavb200_step, the one-launch cavity force + Bussi step, for every kernel variant
+(0 = reduce kernel + apply kernel, 1 = fused persistent kernel with one hand-off, 2 = split-phase
+persistent kernel, the default) on the edge cases of the reference: photon first / middle / last /
+absent / duplicated (src/CavityForceCompute.cc:73-89,120-126,149-156), thermostat groups that are a
+prefix, a window or empty, dt = 0 (src/BussiReservoirThermostat.h:45-48), zero kinetic energy
+(:57-61), sizes below one warp, ragged sizes around the CTA size, launch shapes.
+
+Tolerances: forces / energies 1e-10 relative (BASELINE), velocities and alpha 1e-12 relative, photon
+index, zero components and untouched velocities exact; the three variants must agree BIT FOR BIT
+(same per-thread summation orders)."""
+import numpy as np
+import pytest
+
+from cav_hoomd_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+KT, TAU, DT = synth.KT_100K, synth.TAU_5PS, synth.DT_1FS
+VARIANTS = [0, 1, 2]
+
+
+def run_step(handle, s, first, n, a, omegac=0.01, g=1e-3):
+    p = capi.Params.make(omegac, g)
+    dev = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+    d_f = capi.DeviceArray.from_numpy(np.full((s.N, 4), np.nan))
+    handle.bussi_reset()
+    handle.step(dev["pos"], dev["charge"], dev["image"], d_f, dev["vel"], s.N, s.box, s.L_typeid, p, first, n, a)
+    en, dip, ph = handle.force_read()
+    return d_f.numpy(), dev["vel"].numpy(), en, dip, ph, handle.bussi_read()
+
+
+def check_against_oracle(coracle, s, first, n, a, out, omegac=0.01, g=1e-3):
+    f, v, en, dip, ph, bo = out
+    ref = coracle.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, omegac, g)
+    assert ph == ref["photon_idx"]
+    scale = max(np.abs(ref["force"]).max(), 1e-300)
+    assert np.abs(f - ref["force"]).max() <= 1e-10 * scale
+    assert np.array_equal(f[:, 2] == 0.0, ref["force"][:, 2] == 0.0) and np.all(f[:, 3] == 0.0)
+    assert np.allclose(en, ref["energies"], rtol=1e-10, atol=0)
+    vref = s.vel.copy()
+    if n > 0 and a.deltaT != 0.0:
+        idx = np.arange(first, first + n, dtype=np.uint32)
+        alpha_ref, ke_ref = coracle.bussi_step(vref, idx, a.dof, a.deltaT, a.kT, a.tau, a.r_normal, a.gamma_draw, np.zeros(2))
+        assert abs(bo["alpha"] - alpha_ref) <= 1e-12 * abs(alpha_ref)
+    assert np.allclose(v, vref, rtol=1e-12, atol=0)
+    # velocities outside the thermostatted window are untouched, bit for bit
+    outside = np.ones(s.N, dtype=bool)
+    outside[first:first + n] = False
+    assert np.array_equal(v[outside].view(np.uint64), s.vel[outside].view(np.uint64))
+
+
+def args_for(n_group, dt=DT, **kw):
+    dof = max(3.0 * n_group - 3.0, 0.0)
+    return capi.BussiArgs(KT, TAU, dt, dof, kw.get("r_normal", 0.3), kw.get("gamma_draw", max(dof - 1.0, 0.0) / 2.0 * 1.001))
+
+
+@pytest.mark.parametrize("n_mol", [1, 2, 31, 32, 33, 383, 384, 385, 1000, 65537, 113665])
+def test_step_sizes_all_variants_bitwise(handle, coracle, n_mol):
+    s = synth.make_system(n_mol)
+    a = args_for(n_mol)
+    outs = []
+    for variant in VARIANTS:
+        handle.set_tuning(variant=variant, threads=384, ctas_per_sm=2, unroll=2)
+        outs.append(run_step(handle, s, 0, n_mol, a))
+        check_against_oracle(coracle, s, 0, n_mol, a, outs[-1])
+    for o in outs[1:]:
+        assert np.array_equal(o[0].view(np.uint64), outs[0][0].view(np.uint64))
+        assert np.array_equal(o[1].view(np.uint64), outs[0][1].view(np.uint64))
+        assert np.array_equal(o[2], outs[0][2]) and o[5]["alpha"] == outs[0][5]["alpha"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("photon", ["first", "middle", "last", "absent", "duplicated"])
+def test_step_photon_placement(handle, coracle, photon, variant):
+    handle.set_tuning(variant=variant, threads=384, ctas_per_sm=2, unroll=2)
+    n_mol = 20011
+    s = synth.make_system(n_mol, photon=photon)
+    # thermostat the molecular particles only when they are a contiguous range; else everything
+    first, n = (1, n_mol) if photon == "first" else (0, n_mol if photon in ("last", "absent") else s.N)
+    a = args_for(n)
+    check_against_oracle(coracle, s, first, n, a, run_step(handle, s, first, n, a))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("first,n", [(0, 0), (0, 1), (0, 5000), (1234, 5000), (19999, 2), (7, 20001 - 7)])
+def test_step_group_windows(handle, coracle, first, n, variant):
+    handle.set_tuning(variant=variant, threads=384, ctas_per_sm=2, unroll=2)
+    s = synth.make_system(20000)
+    a = args_for(n)
+    check_against_oracle(coracle, s, first, n, a, run_step(handle, s, first, n, a))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_step_dt_zero_and_zero_ke(handle, coracle, variant):
+    handle.set_tuning(variant=variant, threads=384, ctas_per_sm=2, unroll=2)
+    s = synth.make_system(5000)
+    # dt == 0: the thermostat half is a no-op (alpha = 1), the force half still runs
+    a0 = args_for(5000, dt=0.0)
+    out = run_step(handle, s, 0, 5000, a0)
+    check_against_oracle(coracle, s, 0, 5000, a0, out)
+    assert np.array_equal(out[1].view(np.uint64), s.vel.view(np.uint64))
+    # zero kinetic energy with dof != 0: error flag (the reference throws), velocities untouched, forces correct
+    s.vel[:, :3] = 0.0
+    a = args_for(5000)
+    f, v, en, dip, ph, bo = run_step(handle, s, 0, 5000, a)
+    assert bo["err"] == 1.0 and np.all(v[:, :3] == 0.0)
+    ref = coracle.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, 0.01, 1e-3)
+    assert np.abs(f - ref["force"]).max() <= 1e-10 * np.abs(ref["force"]).max()
+    handle.bussi_reset()
+
+
+@pytest.mark.parametrize("threads,ctas,unroll", [(128, 2, 2), (256, 4, 2), (384, 1, 2), (512, 1, 4), (768, 1, 2), (1024, 1, 2), (256, 1, 8)])
+def test_step_launch_shapes_split_kernel(handle, coracle, threads, ctas, unroll):
+    handle.set_tuning(variant=2, threads=threads, ctas_per_sm=ctas, unroll=unroll)
+    s = synth.make_system(150001)
+    a = args_for(150001)
+    check_against_oracle(coracle, s, 0, 150001, a, run_step(handle, s, 0, 150001, a))
+    handle.set_tuning(variant=2, threads=384, ctas_per_sm=2, unroll=2)
+
+
+def test_step_back_to_back_epochs(handle, coracle):
+    """Many launches in a row on alternating systems and grid sizes: the hand-off's epoch tagging must
+    never let a record of an earlier launch pass for a current one."""
+    handle.set_tuning(variant=2, threads=384, ctas_per_sm=2, unroll=2)
+    systems = [synth.make_system(n, replica=k) for k, n in enumerate((300, 70001, 5, 20000))]
+    p = capi.Params.make(0.01, 1e-3)
+    devs = []
+    for s in systems:
+        d = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+        d["force"] = capi.DeviceArray((s.N, 4), np.float64)
+        devs.append(d)
+    refs = [coracle.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, 0.01, 1e-3) for s in systems]
+    st = capi.Stream()
+    for it in range(40):
+        k = it % len(systems)
+        s, d = systems[k], devs[k]
+        a = capi.BussiArgs(KT, TAU, 0.0, 3.0 * (s.N - 1) - 3.0, 0.0, 1.0)  # dt = 0: velocities stay put
+        handle.step(d["pos"], d["charge"], d["image"], d["force"], d["vel"], s.N, s.box, s.L_typeid, p, 0, s.N - 1, a, st.ptr)
+        if it >= 36:
+            f = d["force"].numpy(st.ptr)
+            assert np.abs(f - refs[k]["force"]).max() <= 1e-10 * np.abs(refs[k]["force"]).max()
