@@ -211,6 +211,32 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         return 0;
         }
 
+    if (!FORCE && BUSSI && !b.rescale && h->tune.variant >= 1)
+        {
+        // kinetic energy only (cavb200_bussi_ke, what getRescalingFactorsOne needs when HOOMD applies
+        // the rescale itself): nothing is applied afterwards, so no CTA has to wait for the others --
+        // reduce kernel alone, the last CTA to take a ticket folds the records and publishes Scalars
+        const int grid = (int)(want < (unsigned long long)max_grid ? want : (unsigned long long)max_grid);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(threads);
+        cfg.stream = s;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = h->tune.pdl ? 1 : 0;
+        ForceIn ff = f;
+        BussiIn bb = b;
+        Partial* recs = h->partials;
+        Scalars* sca = h->scalars;
+        unsigned long long* ticket = h->counters + 4;
+        void* a1[] = {&ff, &bb, &recs, &sca, &fin_dev, &ticket};
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_reduce<FORCE, BUSSI, UNROLL, LB>, a1));
+        h->launches += 1;
+        return 0;
+        }
+
     if (h->tune.variant >= 1 && h->coop_supported)
         {
         int per_sm = 0;

@@ -209,3 +209,28 @@ def test_step_host_buffers(handle, coracle):
         assert np.allclose(va, vref, rtol=1e-12, atol=0)
         assert np.allclose(en, ref["energies"], rtol=1e-10)
         assert bo["err"] == 0.0
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("n,first,use_list", [(1, 0, False), (33, 0, False), (1000, 7, False), (262145, 0, False),
+                                               (50001, 0, True), (0, 0, False)])
+def test_bussi_ke_only(handle, n, first, use_list, variant):
+    """cavb200_bussi_ke = the kinetic energy getRescalingFactorsOne reads from ComputeThermo
+    (reference src/BussiReservoirThermostat.h:50-55): 1/2 sum m|v|^2 over the group, velocities untouched.
+    Tolerance 1e-12 relative (tree sum vs NumPy pairwise sum of positive terms)."""
+    handle.set_tuning(variant=variant, threads=384, ctas_per_sm=2, unroll=2)
+    s = synth.make_system(max(n + first, 300000 if use_list else 1))
+    d_vel = capi.DeviceArray.from_numpy(s.vel)
+    if use_list:
+        idx = np.arange(1, 2 * n, 2, dtype=np.uint32)
+        d_idx = capi.DeviceArray.from_numpy(idx)
+        handle.bussi_ke(d_vel, d_idx, 0, n)
+        sel = s.vel[idx]
+    else:
+        handle.bussi_ke(d_vel, None, first, n)
+        sel = s.vel[first:first + n]
+    ke = 0.5 * np.sum(sel[:, 3] * np.sum(sel[:, :3] ** 2, axis=1))
+    got = handle.bussi_read()["ke"]
+    assert abs(got - ke) <= 1e-12 * max(ke, 1e-300)
+    assert np.array_equal(d_vel.numpy().view(np.uint64), s.vel.view(np.uint64))
+    handle.set_tuning(variant=2)

@@ -12,7 +12,7 @@ a = capi.BussiArgs(synth.KT_100K, synth.TAU_5PS, synth.DT_1FS, dof, 0.1, (dof - 
 st = capi.Stream()
 for variant, threads, ctas in ((2, 384, 2),):
     h.set_tuning(variant=variant, threads=threads, ctas_per_sm=ctas, unroll=2)
-    for kind, nb in (("step", 148),):
+    for kind, nb in (("step", 148), ("bussi", 64)):
         for k in range(10):
             call(h, kind, systems[k % 8], base, n_mol, p, a, st.ptr)
         capi.sync()
