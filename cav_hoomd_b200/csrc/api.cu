@@ -133,7 +133,6 @@ int cavb200_create(cavb200_handle** out, int device)
     h->tune.threads = 384;
     h->tune.ctas_per_sm = 2;
     h->tune.unroll = 2;
-    h->tune.prefetch = 0;
     h->tune.pdl = 1;
     h->tune.rhok_threads = 256;
     h->tune.rhok_kblock = 8;
@@ -175,7 +174,6 @@ static int* tuning_slot(cavb::Tuning* t, const char* key)
     if (!strcmp(key, "threads")) return &t->threads;
     if (!strcmp(key, "ctas_per_sm")) return &t->ctas_per_sm;
     if (!strcmp(key, "unroll")) return &t->unroll;
-    if (!strcmp(key, "prefetch")) return &t->prefetch;
     if (!strcmp(key, "stamps")) return &t->stamps;
     if (!strcmp(key, "pdl")) return &t->pdl;
     if (!strcmp(key, "rhok_threads")) return &t->rhok_threads;

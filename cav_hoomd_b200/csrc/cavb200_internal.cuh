@@ -74,11 +74,10 @@ struct __align__(16) Scalars
 
 struct Tuning
     {
-    int variant;         // 0 = reduce kernel + apply kernel, 1 = one cooperative persistent kernel
+    int variant;         // 0 = reduce kernel + apply kernel, 1 = fused persistent kernel, 2 = split-phase step kernel (default)
     int threads;         // CTA size of the streaming kernels (256 / 512 / 1024)
     int ctas_per_sm;     // resident CTAs per SM the grid is sized for
     int unroll;          // independent particle loads in flight per thread (1, 2 or 4)
-    int prefetch;        // cooperative variant: issue the apply pass's first loads before the barrier
     int pdl;             // launch with programmatic stream serialization (hides the launch gap)
     int stamps;          // debug: record per-CTA phase timestamps of the cooperative kernel
     int rhok_threads;
@@ -130,11 +129,7 @@ __device__ __forceinline__ double4 ld256_stream(const double4* p)
     double4 r;
     // read once per step: do not keep it in L1, and mark it first to leave L2 (the 126 MB L2 is wanted
     // for the charge / velocity lines the apply pass reads again and for the dirty output lines)
-#ifndef CAVB_NO_L2_HINTS
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
-#else
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-#endif
                  : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
                  : "l"(p));
     return r;
@@ -187,36 +182,18 @@ __device__ __forceinline__ void st256(double4* p, const double4& v)
 // output nobody in this library reads again (the force array)
 __device__ __forceinline__ void st256_stream(double4* p, const double4& v)
     {
-#ifndef CAVB_NO_L2_HINTS
     asm volatile("st.global.L2::evict_first.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w)
                  : "memory");
-#else
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
-#endif
     }
 // programmatic dependent launch: wait for the previous kernel of the stream / let the next one start
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
-    {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-    }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
     {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-    }
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
-    {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-    }
-__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v)
-    {
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
     }
 __device__ __forceinline__ unsigned long long atom_acq_rel_add_u64(unsigned long long* p, unsigned long long v)
     {
@@ -224,9 +201,6 @@ __device__ __forceinline__ unsigned long long atom_acq_rel_add_u64(unsigned long
     asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
     return old;
     }
-// acq_rel fence at gpu scope (MEMBAR.ALL.GPU): cheaper than __threadfence()'s sequentially
-// consistent MEMBAR.SC.GPU and all the record/flag protocol needs
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 // NOTE (measured, round 1): polling with a weak ld.global.cg does NOT work on sm_100 -- a thread
 // whose first poll missed kept reading the stale value until the 2 s guard fired.  Polls and record
 // reads therefore use strong (relaxed, gpu-scope) loads.

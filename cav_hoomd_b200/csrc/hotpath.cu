@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         publish_record(recsB + blockIdx.x, sc.rec, epoch);
     if (my_stamps)
         my_stamps[2] = globaltimer_ns();
-    combine_phase<true, false, true, true>(recsF, (int)gridDim.x, epoch, f, b, sc, scalars, blockIdx.x == 0);
+    // (debug stamps of the combine's inner steps go to a second bank, 1024 CTAs further on)
+    combine_phase<true, false, true, true>(recsF, (int)gridDim.x, epoch, f, b, sc, scalars, blockIdx.x == 0,
+                                           my_stamps ? my_stamps + 8 * 1024 : nullptr);
     if (my_stamps)
         my_stamps[3] = globaltimer_ns();
     const bool timeout_f = sc.fin.timeout != 0;

@@ -173,79 +173,17 @@ __device__ __forceinline__ void take_particle(Acc& a, unsigned int i, const doub
         }
     if (!aside)
         {
-#ifdef CAVB_EXP_PLAIN_SUM
-        a.dhi[0] += t[0];
-        a.dhi[1] += t[1];
-        a.dhi[2] += t[2];
-#else
         two_sum_acc(a.dhi[0], a.dlo[0], t[0]);
         two_sum_acc(a.dhi[1], a.dlo[1], t[1]);
         two_sum_acc(a.dhi[2], a.dlo[2], t[2]);
-#endif
-        }
-    }
-
-template<int UNROLL> __device__ __forceinline__ void reduce_force(Acc& a, const ForceIn& f)
-    {
-#ifdef CAVB_EXP_CHUNK
-    const unsigned long long per = ((f.N + gridDim.x - 1) / gridDim.x + 31) & ~31ull;
-    const unsigned long long stride = blockDim.x;
-    unsigned long long i = per * blockIdx.x + threadIdx.x;
-    const unsigned long long N = min((unsigned long long)f.N, per * (blockIdx.x + 1ull));
-#else
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long N = f.N;
-#endif
-    if (UNROLL > 1)
-        {
-        for (; i + (UNROLL - 1) * stride < N; i += UNROLL * stride)
-            {
-            double4 p[UNROLL];
-            double c[UNROLL];
-            int ix[UNROLL], iy[UNROLL], iz[UNROLL];
-#pragma unroll
-            for (int k = 0; k < UNROLL; k++)
-                {
-                const unsigned long long j = i + k * stride;
-                p[k] = ld256_stream(f.pos + j);
-                c[k] = __ldg(f.charge + j);
-#ifdef CAVB_EXP_NO_IMAGE
-                ix[k] = iy[k] = iz[k] = 0;
-#else
-                ix[k] = __ldg(f.image + 3 * j + 0);
-                iy[k] = __ldg(f.image + 3 * j + 1);
-                iz[k] = __ldg(f.image + 3 * j + 2);
-#endif
-                }
-#pragma unroll
-            for (int k = 0; k < UNROLL; k++)
-                take_particle(a, (unsigned int)(i + k * stride), p[k], c[k], ix[k], iy[k], iz[k], f);
-            }
-        }
-    for (; i < N; i += stride)
-        {
-        const double4 p = ld256_stream(f.pos + i);
-        const double c = __ldg(f.charge + i);
-        const int ix = __ldg(f.image + 3 * i + 0);
-        const int iy = __ldg(f.image + 3 * i + 1);
-        const int iz = __ldg(f.image + 3 * i + 2);
-        take_particle(a, (unsigned int)i, p, c, ix, iy, iz, f);
         }
     }
 
 template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const BussiIn& b)
     {
-#ifdef CAVB_EXP_CHUNK
-    const unsigned long long per = ((b.n + gridDim.x - 1) / gridDim.x + 31) & ~31ull;
-    const unsigned long long stride = blockDim.x;
-    unsigned long long j = per * blockIdx.x + threadIdx.x;
-    const unsigned long long n = min((unsigned long long)b.n, per * (blockIdx.x + 1ull));
-#else
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long n = b.n;
-#endif
     double ke[UNROLL > 1 ? UNROLL : 1];
 #pragma unroll
     for (int k = 0; k < (UNROLL > 1 ? UNROLL : 1); k++)

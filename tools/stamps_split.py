@@ -71,6 +71,12 @@ def main():
             t0 = s[:, 0].min()
             ph = [s[:, i + 1] - s[:, i] for i in range(6)]
             print(f"{k:6d} | {ev:6.2f} | " + " | ".join(f"{np.median(x):6.2f} {x.max():6.2f}" for x in ph) + f" | {s[:, 6].max() - t0:6.2f}")
+            raw = h.debug_stamps(1024 + G).astype(np.float64) * 1e-3
+            c0 = raw[:G, 2]  # start of the dipole combine = end of the KE pass
+            d2 = raw[1024:1024 + G]
+            print("         dipole combine, medians: records loaded+voted %.2f | trees+barrier %.2f | fold+vote in warp 0 %.2f | finalize %.2f | to end %.2f"
+                  % (np.median(d2[:, 2] - c0), np.median(d2[:, 5] - d2[:, 2]), np.median(d2[:, 6] - d2[:, 5]),
+                     np.median(d2[:, 7] - d2[:, 6]), np.median(raw[:G, 3] - d2[:, 7])))
             if variant == 4:
                 rel = s - t0
                 names = ["start", "dipR+pub", "KE pub", "F: Dq ready", "F: forces done", "K: alpha ready", "end"]
