@@ -67,6 +67,13 @@ _SIGNATURES = {
     "cavb200_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _u32, _u32, _BP, _vp]),
     "cavb200_nve_kick_drift": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _dbl, _vp]),
     "cavb200_nve_half_kick": (C.c_int, [_vp, _vp, _vp, _u32, _dbl, _vp]),
+    "cavb200_nvt_step_one": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _dbl, _u32, _u32, _BP, _vp]),
+    "cavb200_nvt_step_two": (C.c_int, [_vp, _vp, _vp, _u32, _dbl, _u32, _u32, _vp]),
+    "cavb200_force_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _vp]),
+    "cavb200_rank1_read": (C.c_int, [_vp, _dp, _dp, C.POINTER(C.c_int32), C.POINTER(_u32), _vp]),
+    "cavb200_net_force_add_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _u32, _dbl, _vp]),
+    "cavb200_nvt_step_one_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _dbl, _u32, _dbl, _u32, _u32, _BP, _vp]),
+    "cavb200_nvt_step_two_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _dbl, _u32, _dbl, _u32, _u32, _vp]),
     "cavb200_rhok": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _u32, _vp, _u32, _vp, _vp]),
     "cavb200_fkt": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp]),
     "cavb200_shard_nccl_unique_id": (C.c_int, [_vp]),
@@ -76,6 +83,9 @@ _SIGNATURES = {
     "cavb200_shard_set_mode": (C.c_int, [_vp, C.c_int]),
     "cavb200_shard_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u64, _dbl, _dbl, _dbl, _u32, _PP, _u32, _u32,
                                      _BP, _vp]),
+    "cavb200_step_host_submit": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _u32, _u32,
+                                           _BP]),
+    "cavb200_step_host_wait": (C.c_int, [_vp, _u32, _dp, _dp]),
     "cavb200_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _u32, _u32, _BP,
                                     _dp, _dp]),
     "cavb200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
@@ -350,10 +360,60 @@ class Handle:
                                          n_group, C.byref(bussi), en, bo), "cavb200_step_host")
         return np.array(en[:]), dict(ke=bo[0], alpha=bo[1], instantaneous=bo[2], cumulative=bo[3], err=bo[4])
 
+    def step_host_submit(self, slot, pos, charge, image, force, vel, N, box, L_typeid, params, group_first, n_group,
+                         bussi):
+        check(self.lib.cavb200_step_host_submit(self.h, slot, _ptr(pos), _ptr(charge), _ptr(image), _ptr(force),
+                                                _ptr(vel), N, box[0], box[1], box[2], L_typeid & 0xFFFFFFFF,
+                                                C.byref(params), group_first, n_group, C.byref(bussi)),
+              "cavb200_step_host_submit")
+
+    def step_host_wait(self, slot):
+        en = (C.c_double * 3)()
+        bo = (C.c_double * 5)()
+        check(self.lib.cavb200_step_host_wait(self.h, slot, en, bo), "cavb200_step_host_wait")
+        return np.array(en[:]), dict(ke=bo[0], alpha=bo[1], instantaneous=bo[2], cumulative=bo[3], err=bo[4])
+
     # -- NVE harness ------------------------------------------------------------------------------
     def nve_kick_drift(self, pos, vel, force, N, dt, stream=None):
         check(self.lib.cavb200_nve_kick_drift(self.h, _ptr(pos), _ptr(vel), _ptr(force), N, dt, stream),
               "cavb200_nve_kick_drift")
+
+    def nvt_step_one(self, pos, vel, force, N, dt, group_first, n_group, bussi=None, stream=None):
+        check(self.lib.cavb200_nvt_step_one(self.h, _ptr(pos), _ptr(vel), _ptr(force), N, dt, group_first, n_group,
+                                            C.byref(bussi) if bussi is not None else None, stream), "cavb200_nvt_step_one")
+
+    def nvt_step_two(self, vel, force, N, dt, group_first, n_group, stream=None):
+        check(self.lib.cavb200_nvt_step_two(self.h, _ptr(vel), _ptr(force), N, dt, group_first, n_group, stream),
+              "cavb200_nvt_step_two")
+
+    # -- rank-1 cavity force ---------------------------------------------------
+    def force_rank1(self, pos, charge, image, N, box, L_typeid, params: Params, stream=None):
+        check(self.lib.cavb200_force_rank1(self.h, _ptr(pos), _ptr(charge), _ptr(image), N, box[0], box[1], box[2],
+                                           L_typeid & 0xFFFFFFFF, C.byref(params), stream), "cavb200_force_rank1")
+
+    def rank1_read(self, stream=None):
+        dq, fl = (C.c_double * 2)(), (C.c_double * 3)()
+        ph, nl = C.c_int32(0), C.c_uint32(0)
+        check(self.lib.cavb200_rank1_read(self.h, dq, fl, C.byref(ph), C.byref(nl), stream), "cavb200_rank1_read")
+        return np.array(dq[:]), np.array(fl[:]), int(ph.value), int(nl.value)
+
+    def net_force_add_rank1(self, net_force, charge, pos, N, L_typeid, couplstr, stream=None):
+        check(self.lib.cavb200_net_force_add_rank1(self.h, _ptr(net_force), _ptr(charge), _ptr(pos), N,
+                                                   L_typeid & 0xFFFFFFFF, couplstr, stream),
+              "cavb200_net_force_add_rank1")
+
+    def nvt_step_one_rank1(self, pos, vel, force_other, charge, N, dt, L_typeid, couplstr, group_first, n_group,
+                           bussi=None, stream=None):
+        check(self.lib.cavb200_nvt_step_one_rank1(self.h, _ptr(pos), _ptr(vel), _ptr(force_other), _ptr(charge), N, dt,
+                                                  L_typeid & 0xFFFFFFFF, couplstr, group_first, n_group,
+                                                  C.byref(bussi) if bussi is not None else None, stream),
+              "cavb200_nvt_step_one_rank1")
+
+    def nvt_step_two_rank1(self, vel, force_other, charge, pos, N, dt, L_typeid, couplstr, group_first, n_group,
+                           stream=None):
+        check(self.lib.cavb200_nvt_step_two_rank1(self.h, _ptr(vel), _ptr(force_other), _ptr(charge), _ptr(pos), N, dt,
+                                                  L_typeid & 0xFFFFFFFF, couplstr, group_first, n_group, stream),
+              "cavb200_nvt_step_two_rank1")
 
     def nve_half_kick(self, vel, force, N, dt, stream=None):
         check(self.lib.cavb200_nve_half_kick(self.h, _ptr(vel), _ptr(force), N, dt, stream), "cavb200_nve_half_kick")

@@ -43,9 +43,10 @@ namespace
 inline bool misaligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
 
 int fill_force(ForceIn& f, const double* pos, const double* charge, const int32_t* image, double* force, uint32_t N,
-               double Lx, double Ly, double Lz, uint32_t L_typeid, const cavb200_params* p, uint64_t index_offset)
+               double Lx, double Ly, double Lz, uint32_t L_typeid, const cavb200_params* p, uint64_t index_offset,
+               bool need_force = true)
     {
-    if (!pos || !charge || !image || !force || !p)
+    if (!pos || !charge || !image || (need_force && !force) || !p)
         return (int)cudaErrorInvalidValue;
     if (misaligned(pos, 32) || misaligned(force, 32) || misaligned(charge, 8) || misaligned(image, 4))
         return (int)cudaErrorMisalignedAddress;
@@ -223,6 +224,41 @@ int cavb200_force(cavb200_handle* h, const double* pos, const double* charge, co
     if (rc)
         return rc;
     return launch_hotpath(h, &f, nullptr, (cudaStream_t)stream);
+    }
+
+int cavb200_force_rank1(cavb200_handle* h, const double* pos, const double* charge, const int32_t* image, uint32_t N,
+                        double Lx, double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params, void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    ForceIn f;
+    int rc = fill_force(f, pos, charge, image, nullptr, N, Lx, Ly, Lz, L_typeid, params, 0, false);
+    if (rc)
+        return rc;
+    return launch_hotpath(h, &f, nullptr, (cudaStream_t)stream);
+    }
+
+int cavb200_rank1_read(cavb200_handle* h, double Dq[2], double F_L[3], int32_t* photon_idx, uint32_t* n_L, void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    Scalars s;
+    CAVB_CHECK(cudaMemcpyAsync(&s, h->scalars, sizeof(Scalars), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CAVB_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int k = 0; k < 3; k++)
+        {
+        if (Dq && k < 2)
+            Dq[k] = s.Dq[k];
+        if (F_L)
+            F_L[k] = s.FL[k];
+        }
+    if (photon_idx)
+        *photon_idx = (int32_t)s.photon_idx;
+    if (n_L)
+        *n_L = s.n_L;
+    return 0;
     }
 
 int cavb200_force_read(cavb200_handle* h, double energies[3], double dipole[3], int32_t* photon_idx, void* stream)

@@ -98,6 +98,8 @@ struct ShardState
     };
     } // namespace cavb
 
+#define CAVB_HOST_SLOTS 4
+
 struct cavb200_handle
     {
     int device;
@@ -105,17 +107,20 @@ struct cavb200_handle
     int coop_supported;
     cavb::Partial* partials;          // MAX_PARTIALS records
     cavb::Scalars* scalars;           // 1 record
-    unsigned long long* counters;     // [2] hand-off epoch, [4] reduce-pass ticket, [8..] Final (variant 0)
+    unsigned long long* counters;     // [2] hand-off epoch, [4] reduce-pass ticket, [8..] Final (variant 0), [32..] Final (rank-1)
     uint64_t launches;
     unsigned long long* stamps;       // MAX_PARTIALS x 8 timestamps (debug)
     cavb::Tuning tune;
     cavb::ShardState shard;
     // host-buffer pipeline staging (grown on demand, owned)
-    void* stage[5];
-    uint64_t stage_bytes[5];
-    cudaStream_t copy_streams[3];
+    void* stage[CAVB_HOST_SLOTS][5];
+    uint64_t stage_bytes[CAVB_HOST_SLOTS][5];
+    cudaStream_t copy_streams[3];     // copy-in, kernels, copy-out
     cudaEvent_t copy_events[64];
     int copy_ready;
+    int slot_used[CAVB_HOST_SLOTS];
+    cavb::Scalars* slot_scalars;      // device, one per slot
+    cavb::Scalars* slot_scalars_host; // pinned, one per slot
     // F(k,t) workspace
     double* rhok_partials;
     uint64_t rhok_partials_bytes;
@@ -270,6 +275,10 @@ struct BussiIn
     };
 
 void fill_force_constants(ForceIn& f);
+// device slot of the Final record cavb200_force_rank1 leaves for the rank-1 consumers (nve.cu); apart
+// from the variant-0 slot at counters + 8, which every reduce-only launch overwrites
+struct Final;
+inline const Final* rank1_final(const cavb200_handle* h) { return reinterpret_cast<const Final*>(h->counters + 32); }
 void fill_bussi_constants(BussiIn& b, const cavb200_bussi_args* a);
 int launch_hotpath(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cudaStream_t s);
 int launch_shard_step(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cudaStream_t s);

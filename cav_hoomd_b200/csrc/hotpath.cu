@@ -213,7 +213,11 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         return 0;
         }
 
-    if (!FORCE && BUSSI && !b.rescale && h->tune.variant >= 1)
+    // rank-1 mode (cavb200_force_rank1): no force array -- dipole reduce, fold, Scalars + Final
+    const bool rank1 = FORCE && !BUSSI && f.force == nullptr;
+    if (rank1)
+        fin_dev = const_cast<Final*>(rank1_final(h));
+    if (rank1 || (!FORCE && BUSSI && !b.rescale && h->tune.variant >= 1))
         {
         // kinetic energy only (cavb200_bussi_ke, what getRescalingFactorsOne needs when HOOMD applies
         // the rescale itself): nothing is applied afterwards, so no CTA has to wait for the others --

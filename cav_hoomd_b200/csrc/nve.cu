@@ -1,10 +1,158 @@
 // nve.cu -- minimal velocity-Verlet harness around the cavity force (energy-drift comparison).
 // Same arithmetic as oracle/cavity_oracle.c orc_nve_step: hm = 0.5*dt/m; v = v + hm*f; r = r + dt*v,
 // each product and sum rounded separately (no FMA) so that both arms integrate identically.
-#include "cavb200_internal.cuh"
+//
+// Thermostatted variant (cavb200_nvt_step_one / _two): the Bussi rescale rides on the
+// first half step and the kinetic energy the thermostat needs at the NEXT step is accumulated while the
+// second half step writes the velocities, so the thermostat costs no pass of its own (the standalone
+// cavb200_bussi call moves 64 B/particle, 96 B once the velocities no longer fit L2).  Same arithmetic
+// as oracle/cavity_oracle.c orc_nvt_step.  This is the repo's own harness, NOT HOOMD's integrator.
+#include "hotpath.cuh"
 
 namespace cavb
     {
+// step one: alpha from the KE left in Scalars by the previous step two (or by cavb200_bussi_ke);
+// group: v <- alpha v;  all: v += dt/2 f/m;  r += dt v.  Purely element-wise: no hand-off.
+// RANK1: the cavity force is never stored -- it is rank-1, F_i = (-g c_i) Dq
+// (reference src/CavityForceCompute.cc:188-200), so the kick forms it from the charge and the Final
+// record cavb200_force_rank1 left on the device and adds it to the other forces (force may be NULL).
+struct Rank1In
+    {
+    const double* charge;
+    const Final* fin;
+    ForceIn f; // pos (type look-up, only when several 'L' particles exist), L_typeid, g
+    };
+
+template<bool RANK1>
+__device__ __forceinline__ double4 kick_force(const double4* force, unsigned long long i, const Rank1In& r, const Final& fin)
+    {
+    if (!RANK1)
+        return ld256(force + i);
+    double4 fc = force_of(i, __ldg(r.charge + i), fin, r.f);
+    if (force)
+        {
+        const double4 fo = ld256(force + i);
+        fc.x = __dadd_rn(fo.x, fc.x);
+        fc.y = __dadd_rn(fo.y, fc.y);
+        fc.z = __dadd_rn(fo.z, fc.z);
+        fc.w = fo.w; // potential-energy slot of the other forces; the cavity term's is 0 (:145,180)
+        }
+    return fc;
+    }
+
+template<bool RANK1>
+__global__ void __launch_bounds__(256)
+    k_nvt_one(double4* pos, double4* vel, const double4* force, uint32_t N, double dt, BussiIn b, Scalars* scalars,
+              Rank1In r1)
+    {
+    __shared__ double s_alpha;
+    __shared__ Final s_fin;
+    if (threadIdx.x == 0)
+        {
+        if (RANK1)
+            s_fin = *r1.fin;
+        double alpha = 1.0;
+        if (b.rescale && b.n > 0)
+            {
+            int ok = 1;
+            const double KE = scalars->ke;
+            alpha = bussi_alpha(KE, b, ok);
+            if (blockIdx.x == 0)
+                {
+                if (ok)
+                    {
+                    // BussiReservoirThermostat.h:86-95
+                    const double inst = __dmul_rn(KE, __dadd_rn(1.0, -__dmul_rn(alpha, alpha)));
+                    scalars->alpha = alpha;
+                    scalars->inst = inst;
+                    scalars->cumulative = __dadd_rn(scalars->cumulative, inst);
+                    }
+                else
+                    scalars->err = 1.0; // zero kinetic energy with dof != 0 (:57-61): no rescale
+                }
+            }
+        s_alpha = alpha;
+        }
+    __syncthreads();
+    const double alpha = s_alpha;
+    const unsigned long long lo = b.first, hi = (unsigned long long)b.first + b.n;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+        {
+        double4 v = ld256(vel + i);
+        const double4 f = kick_force<RANK1>(force, i, r1, s_fin);
+        double4 p = ld256(pos + i);
+        if (i >= lo && i < hi)
+            {
+            v.x = __dmul_rn(v.x, alpha);
+            v.y = __dmul_rn(v.y, alpha);
+            v.z = __dmul_rn(v.z, alpha);
+            }
+        const double hm = __ddiv_rn(__dmul_rn(0.5, dt), v.w);
+        v.x = __dadd_rn(v.x, __dmul_rn(hm, f.x));
+        v.y = __dadd_rn(v.y, __dmul_rn(hm, f.y));
+        v.z = __dadd_rn(v.z, __dmul_rn(hm, f.z));
+        p.x = __dadd_rn(p.x, __dmul_rn(dt, v.x));
+        p.y = __dadd_rn(p.y, __dmul_rn(dt, v.y));
+        p.z = __dadd_rn(p.z, __dmul_rn(dt, v.z));
+        st256(vel + i, v);
+        st256(pos + i, p);
+        }
+    }
+
+// step two: all: v += dt/2 f/m, and sum m|v|^2 of the group on the way out; the last CTA to take a
+// ticket folds the CTA records (fixed order) and leaves KE in Scalars for the next step one.
+template<bool RANK1>
+__global__ void __launch_bounds__(256)
+    k_nvt_two(double4* vel, const double4* force, uint32_t N, double dt, BussiIn b, Partial* recs, Scalars* scalars,
+              unsigned long long* ticket, Rank1In r1)
+    {
+    __shared__ BlockScratch sc;
+    __shared__ int s_last;
+    __shared__ Final s_fin;
+    if (threadIdx.x == 0)
+        {
+        sc.flags = 0u;
+        if (RANK1)
+            s_fin = *r1.fin;
+        }
+    if (RANK1)
+        __syncthreads();
+    Acc a;
+    acc_zero(a);
+    const unsigned long long lo = b.first, hi = (unsigned long long)b.first + b.n;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+        {
+        double4 v = ld256(vel + i);
+        const double4 f = kick_force<RANK1>(force, i, r1, s_fin);
+        const double hm = __ddiv_rn(__dmul_rn(0.5, dt), v.w);
+        v.x = __dadd_rn(v.x, __dmul_rn(hm, f.x));
+        v.y = __dadd_rn(v.y, __dmul_rn(hm, f.y));
+        v.z = __dadd_rn(v.z, __dmul_rn(hm, f.z));
+        st256(vel + i, v);
+        if (i >= lo && i < hi)
+            a.ke += v.w * (v.x * v.x + v.y * v.y + v.z * v.z);
+        }
+    ForceIn f0 = {};
+    block_merge<false, true>(a, f0, sc);
+    if (threadIdx.x == 0)
+        {
+        publish_record(recs + blockIdx.x, sc.rec, 0ull);
+        __threadfence();
+        const unsigned long long t = atom_acq_rel_add_u64(ticket, 1ull);
+        s_last = (t == (unsigned long long)gridDim.x - 1);
+        }
+    __syncthreads();
+    if (!s_last)
+        return;
+    BussiIn ke_only = b;
+    ke_only.rescale = 0; // finalize: Scalars.ke = 1/2 sum, nothing else
+    combine_phase<false, true, false, true>(recs, (int)gridDim.x, 0ull, f0, ke_only, sc, scalars, true);
+    if (threadIdx.x == 0)
+        *ticket = 0ull;
+    }
+
 template<bool DRIFT>
 __global__ void __launch_bounds__(256) k_nve(double4* pos, double4* vel, const double4* force, uint32_t N, double dt)
     {
@@ -65,4 +213,162 @@ extern "C" int cavb200_nve_half_kick(cavb200_handle* h, double* vel, const doubl
                                      void* stream)
     {
     return nve_launch(h, nullptr, vel, force, N, dt, (cudaStream_t)stream, false);
+    }
+
+// net_force[i] += cavity force of particle i, formed from the charge: what a net-force
+// summing kernel does with the rank-1 contribution instead of reading a stored force array
+__global__ void __launch_bounds__(256) k_net_force_add_rank1(double4* net, uint32_t N, Rank1In r1)
+    {
+    __shared__ Final s_fin;
+    if (threadIdx.x == 0)
+        s_fin = *r1.fin;
+    __syncthreads();
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+        st256(net + i, kick_force<true>(net, i, r1, s_fin));
+    }
+
+static bool mis32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) != 0; }
+
+static int fill_rank1(cavb200_handle* h, Rank1In& r, const double* charge, const double* pos, uint32_t L_typeid,
+                      double couplstr)
+    {
+    if (!charge || !pos)
+        return (int)cudaErrorInvalidValue;
+    if (mis32(pos) || (reinterpret_cast<uintptr_t>(charge) & 7))
+        return (int)cudaErrorMisalignedAddress;
+    r = Rank1In();
+    r.charge = charge;
+    r.fin = rank1_final(h);
+    r.f.pos = reinterpret_cast<const double4*>(pos);
+    r.f.L_typeid = L_typeid;
+    r.f.g = couplstr;
+    return 0;
+    }
+
+static int nvt_one(cavb200_handle* h, double* pos, double* vel, const double* force, uint32_t N, double dt,
+                   uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, const Rank1In* r1, void* stream)
+    {
+    if (!pos || !vel || (!force && !r1) || (unsigned long long)group_first + n_group > N)
+        return (int)cudaErrorInvalidValue;
+    if (mis32(pos) || mis32(vel) || mis32(force))
+        return (int)cudaErrorMisalignedAddress;
+    BussiIn b = {};
+    b.first = group_first;
+    b.n = n_group;
+    b.rescale = bussi != nullptr && bussi->deltaT != 0.0;
+    if (bussi)
+        fill_bussi_constants(b, bussi);
+    unsigned long long want = ((unsigned long long)N + 255) / 256;
+    const unsigned long long cap = (unsigned long long)h->num_sms * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    if (r1)
+        k_nvt_one<true><<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)pos, (double4*)vel, (const double4*)force, N, dt,
+                                                                b, h->scalars, *r1);
+    else
+        k_nvt_one<false><<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)pos, (double4*)vel, (const double4*)force, N,
+                                                                 dt, b, h->scalars, Rank1In());
+    CAVB_CHECK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+    }
+
+static int nvt_two(cavb200_handle* h, double* vel, const double* force, uint32_t N, double dt, uint32_t group_first,
+                   uint32_t n_group, const Rank1In* r1, void* stream)
+    {
+    if (!vel || (!force && !r1) || (unsigned long long)group_first + n_group > N)
+        return (int)cudaErrorInvalidValue;
+    if (mis32(vel) || mis32(force))
+        return (int)cudaErrorMisalignedAddress;
+    BussiIn b = {};
+    b.first = group_first;
+    b.n = n_group;
+    unsigned long long want = ((unsigned long long)N + 255) / 256;
+    unsigned long long cap = (unsigned long long)h->num_sms * 8;
+    if (cap > (unsigned long long)MAX_PARTIALS)
+        cap = MAX_PARTIALS;
+    const int grid = (int)(want < cap ? want : cap);
+    if (r1)
+        k_nvt_two<true><<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)vel, (const double4*)force, N, dt, b, h->partials,
+                                                                h->scalars, h->counters + 4, *r1);
+    else
+        k_nvt_two<false><<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)vel, (const double4*)force, N, dt, b,
+                                                                 h->partials, h->scalars, h->counters + 4, Rank1In());
+    CAVB_CHECK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+    }
+
+extern "C" int cavb200_nvt_step_one(cavb200_handle* h, double* pos, double* vel, const double* force, uint32_t N, double dt,
+                                    uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    return nvt_one(h, pos, vel, force, N, dt, group_first, n_group, bussi, nullptr, stream);
+    }
+
+extern "C" int cavb200_nvt_step_two(cavb200_handle* h, double* vel, const double* force, uint32_t N, double dt,
+                                    uint32_t group_first, uint32_t n_group, void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    return nvt_two(h, vel, force, N, dt, group_first, n_group, nullptr, stream);
+    }
+
+extern "C" int cavb200_nvt_step_one_rank1(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                                          const double* charge, uint32_t N, double dt, uint32_t L_typeid, double couplstr,
+                                          uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi,
+                                          void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    Rank1In r;
+    const int rc = fill_rank1(h, r, charge, pos, L_typeid, couplstr);
+    if (rc)
+        return rc;
+    return nvt_one(h, pos, vel, force_other, N, dt, group_first, n_group, bussi, &r, stream);
+    }
+
+extern "C" int cavb200_nvt_step_two_rank1(cavb200_handle* h, double* vel, const double* force_other, const double* charge,
+                                          const double* pos, uint32_t N, double dt, uint32_t L_typeid, double couplstr,
+                                          uint32_t group_first, uint32_t n_group, void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    Rank1In r;
+    const int rc = fill_rank1(h, r, charge, pos, L_typeid, couplstr);
+    if (rc)
+        return rc;
+    return nvt_two(h, vel, force_other, N, dt, group_first, n_group, &r, stream);
+    }
+
+extern "C" int cavb200_net_force_add_rank1(cavb200_handle* h, double* net_force, const double* charge, const double* pos,
+                                           uint32_t N, uint32_t L_typeid, double couplstr, void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    if (!net_force)
+        return (int)cudaErrorInvalidValue;
+    if (mis32(net_force))
+        return (int)cudaErrorMisalignedAddress;
+    Rank1In r;
+    const int rc = fill_rank1(h, r, charge, pos, L_typeid, couplstr);
+    if (rc)
+        return rc;
+    unsigned long long want = ((unsigned long long)N + 255) / 256;
+    const unsigned long long cap = (unsigned long long)h->num_sms * 8;
+    k_net_force_add_rank1<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>((double4*)net_force, N, r);
+    CAVB_CHECK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
     }

@@ -148,6 +148,48 @@ int cavb200_nve_kick_drift(cavb200_handle* h, double* pos, double* vel, const do
                            void* stream);
 int cavb200_nve_half_kick(cavb200_handle* h, double* vel, const double* force, uint32_t N, double dt, void* stream);
 
+/* Thermostatted harness step (not a reference function, not HOOMD's integrator):
+ * the Bussi rescale rides on the first half step and the kinetic energy for the NEXT step is taken
+ * while the second half step writes the velocities, so the thermostat costs no pass of its own.
+ *   step_one:  alpha = compute_rescale_factor(KE, draws) (reference src/BussiReservoirThermostat.h:177-225)
+ *              from the KE the previous step_two (or cavb200_bussi_ke) left on the device, reservoir
+ *              bookkeeping (:86-95);  group [group_first, +n_group): v <- alpha v;
+ *              all N: v += (dt/2) f/m;  r += dt v.      bussi == NULL: alpha = 1 (plain NVE).
+ *   step_two:  all N: v += (dt/2) f/m;  KE = 1/2 sum_group m|v|^2 -> device (cavb200_bussi_read()[0]).
+ * A step is  step_one ; cavb200_force ; step_two.  Call cavb200_bussi_ke once before the first step. */
+int cavb200_nvt_step_one(cavb200_handle* h, double* pos, double* vel, const double* force, uint32_t N, double dt,
+                         uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, void* stream);
+int cavb200_nvt_step_two(cavb200_handle* h, double* vel, const double* force, uint32_t N, double dt,
+                         uint32_t group_first, uint32_t n_group, void* stream);
+
+/* ---- rank-1 cavity force -------------------------------------------------------
+ * Every molecular particle's cavity force is the same 2-vector times its charge,
+ *     F_i = (-couplstr * charge_i) * Dq,   Dq = q_xy + (g/K) d_xy
+ * (reference src/CavityForceCompute.cc:183,188-200), so it need not be stored at all:
+ *   cavb200_force_rank1      cavb200_force without the force array: dipole reduce (52 B/particle read,
+ *                            nothing written per particle); energies / dipole / photon index as
+ *                            cavb200_force_read; Dq, F_L stay on the device for the consumers below.
+ *   cavb200_rank1_read       Dq[2], F_L[3] (photon force, :203-207), photon index, number of 'L' particles.
+ *   cavb200_net_force_add_rank1   net_force[i] += F_i formed from charge_i: what HOOMD's net-force sum
+ *                            (Integrator::computeNetForceGPU, upstream) would do with this contribution.
+ *                            The photon gets F_L; further 'L' particles get 0 (pos is only read, for the
+ *                            type, when more than one 'L' particle exists).
+ *   cavb200_nvt_step_one_rank1 / _two_rank1   the harness steps above with the cavity force formed in the
+ *                            kick: f = force_other (NULL = none) + F_i.  Bit-identical to the stored-force
+ *                            steps when force_other == NULL.
+ * All consumers use the result of the LAST cavb200_force_rank1 on this handle. */
+int cavb200_force_rank1(cavb200_handle* h, const double* pos, const double* charge, const int32_t* image, uint32_t N,
+                        double Lx, double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params, void* stream);
+int cavb200_rank1_read(cavb200_handle* h, double Dq[2], double F_L[3], int32_t* photon_idx, uint32_t* n_L, void* stream);
+int cavb200_net_force_add_rank1(cavb200_handle* h, double* net_force, const double* charge, const double* pos,
+                                uint32_t N, uint32_t L_typeid, double couplstr, void* stream);
+int cavb200_nvt_step_one_rank1(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                               const double* charge, uint32_t N, double dt, uint32_t L_typeid, double couplstr,
+                               uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, void* stream);
+int cavb200_nvt_step_two_rank1(cavb200_handle* h, double* vel, const double* force_other, const double* charge,
+                               const double* pos, uint32_t N, double dt, uint32_t L_typeid, double couplstr,
+                               uint32_t group_first, uint32_t n_group, void* stream);
+
 /* ---- F(k,t): density field --------------------------------------------------------------------
  * rho[t][k] = sum_j exp(i kvec[k] . r_j(t)) over ALL N particles of frame t (wrapped positions),
  * the batched form of compute_density_field (reference src/cavitymd/analysis.py:34-47).
@@ -186,11 +228,25 @@ int cavb200_shard_step(cavb200_handle* h, const double* pos, const double* charg
                        void* stream);
 
 /* ---- host-buffer entry points (end-to-end path) ------------------------------------------------
- * Same results as cavb200_step but every array is a HOST pointer: inputs are staged host->device
- * in chunks that overlap the reduce pass, results are copied back while later chunks compute.
- * This is what bench.py's "e2e" measures.  Pinned host memory (cavb200_host_alloc) gives full
- * PCIe speed; pageable memory works but is slower.  Synchronous: returns when outputs are on the
- * host.  energies[3] and bussi_out[5] may be NULL. */
+ * Same results as cavb200_force + cavb200_bussi but every array is a HOST pointer: the library stages
+ * through device buffers it owns (velocities in -> thermostat -> velocities out, overlapped with
+ * positions / charges / images in -> force -> forces out).  This is what bench.py's "e2e" measures.
+ * Pinned host memory (cavb200_host_alloc) gives full PCIe speed; pageable memory works but is slower.
+ *   cavb200_step_host          synchronous: returns when outputs are on the host.
+ *   cavb200_step_host_submit   asynchronous, staging slot 0..3: a driver holding several independent
+ *                              systems on the host (the replicas of examples/05_advanced_run.py:1570-1612)
+ *                              submits system k+1 before waiting for system k, so the next upload runs
+ *                              under this download.  The host arrays must stay valid and untouched
+ *                              until cavb200_step_host_wait(slot) returns; a slot is reusable after that.
+ *   cavb200_step_host_wait     blocks until the slot's outputs are on the host; its energies
+ *                              {harmonic, coupling, dipole self} and {KE, alpha, inst, cumulative, err}.
+ * energies[3] and bussi_out[5] may be NULL.  The reservoir's cumulative energy is per HANDLE (it runs
+ * over every step submitted, in submission order). */
+int cavb200_step_host_submit(cavb200_handle* h, uint32_t slot, const double* pos, const double* charge,
+                             const int32_t* image, double* force, double* vel, uint32_t N, double Lx, double Ly,
+                             double Lz, uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
+                             uint32_t n_group, const cavb200_bussi_args* bussi);
+int cavb200_step_host_wait(cavb200_handle* h, uint32_t slot, double energies[3], double bussi_out[5]);
 int cavb200_step_host(cavb200_handle* h, const double* pos, const double* charge, const int32_t* image,
                       double* force, double* vel, uint32_t N, double Lx, double Ly, double Lz,
                       uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,

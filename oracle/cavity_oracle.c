@@ -266,3 +266,55 @@ void orc_nve_step(double* pos4, double* vel4, const double* charge, const int32_
             v[c] = v[c] + hm * f[c];
         }
     }
+
+double orc_nvt_step(double* pos4, double* vel4, const double* charge, const int32_t* image3,
+                    double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                    double omegac, double couplstr, double phmass, double dt, uint32_t first, uint32_t n,
+                    double dof, double set_T, double tau, double r_normal, double gamma_draw,
+                    double reservoir[2], double* ke_io, double energies[3])
+    {
+    double dip[3];
+    double alpha = 1.0;
+    const double ke = *ke_io;
+    if (n > 0 && dof != 0.0)
+        {
+        if (ke == 0.0)
+            return NAN; /* src/BussiReservoirThermostat.h:57-61 */
+        alpha = orc_bussi_rescale_factor(ke, dof, dt, set_T, tau, r_normal, gamma_draw);
+        const double delta = ke * (1.0 - alpha * alpha); /* :86-95 */
+        reservoir[0] += delta;
+        reservoir[1] = delta;
+        }
+    for (uint32_t i = 0; i < N; i++)
+        {
+        double* v = vel4 + 4 * (size_t)i;
+        double* p = pos4 + 4 * (size_t)i;
+        const double* f = force4 + 4 * (size_t)i;
+        const double hm = 0.5 * dt / v[3];
+        const int in = i >= first && i < first + n;
+        for (int c = 0; c < 3; c++)
+            {
+            double vc = v[c];
+            if (in)
+                vc = vc * alpha;
+            vc = vc + hm * f[c];
+            v[c] = vc;
+            p[c] = p[c] + dt * vc;
+            }
+        }
+    orc_cavity_force(pos4, charge, image3, force4, N, Lx, Ly, Lz, L_typeid, omegac, couplstr,
+                     phmass, energies, dip);
+    double acc = 0.0;
+    for (uint32_t i = 0; i < N; i++)
+        {
+        double* v = vel4 + 4 * (size_t)i;
+        const double* f = force4 + 4 * (size_t)i;
+        const double hm = 0.5 * dt / v[3];
+        for (int c = 0; c < 3; c++)
+            v[c] = v[c] + hm * f[c];
+        if (i >= first && i < first + n)
+            acc += v[3] * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        }
+    *ke_io = 0.5 * acc;
+    return alpha;
+    }

@@ -76,6 +76,20 @@ void orc_nve_step(double* pos4, double* vel4, const double* charge, const int32_
                   double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
                   double omegac, double couplstr, double phmass, double dt, double energies[3]);
 
+/* One step of the thermostatted harness (velocity Verlet with the Bussi rescale folded into the first
+ * half step and the kinetic energy for the NEXT step taken while the second half step writes the
+ * velocities -- SURVEY.md 8f.1).  Not a reference function and not HOOMD's integrator: the harness both
+ * arms share.  *ke_io holds 1/2 sum m|v|^2 of the thermostatted group [first, first+n) on entry (from
+ * the previous step, or orc_kinetic_energy before the first) and on exit.  Sequence:
+ *   alpha = compute_rescale_factor(ke) (src/BussiReservoirThermostat.h:177-225), reservoir bookkeeping
+ *   (:86-95);  group: v <- alpha v;  all: v += dt/2 f/m, r += dt v;  cavity force;  all: v += dt/2 f/m;
+ *   ke = 1/2 sum_group m|v|^2.  Returns alpha (NaN if ke == 0 with dof != 0, :57-61). */
+double orc_nvt_step(double* pos4, double* vel4, const double* charge, const int32_t* image3,
+                    double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                    double omegac, double couplstr, double phmass, double dt, uint32_t first, uint32_t n,
+                    double dof, double set_T, double tau, double r_normal, double gamma_draw,
+                    double reservoir[2], double* ke_io, double energies[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,10 @@ class COracle:
                                      C.c_double, C.c_double, _dp, _dp]
         L.orc_rhok.restype = None
         L.orc_rhok.argtypes = [_dp, C.c_uint32, C.c_uint32, _dp, C.c_uint32, _dp, _dp]
+        L.orc_nvt_step.restype = C.c_double
+        L.orc_nvt_step.argtypes = [_dp, _dp, _dp, _ip, _dp, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_uint32,
+                                   C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, C.c_double,
+                                   C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp]
         L.orc_nve_step.restype = None
         L.orc_nve_step.argtypes = [_dp, _dp, _dp, _ip, _dp, C.c_uint32, C.c_double, C.c_double, C.c_double,
                                    C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double, _dp]
@@ -116,6 +120,16 @@ class COracle:
         im = np.zeros(K)
         self.lib.orc_rhok(_d(pos), pos.shape[1], pos.shape[0], _d(kvec), K, _d(re), _d(im))
         return re + 1j * im
+
+    def nvt_step(self, pos, vel, charge, image, force, box, L_typeid, omegac, couplstr, phmass, dt, first, n, dof, kT,
+                 tau, r_normal, gamma_draw, reservoir, ke_io):
+        """One thermostatted harness step (orc_nvt_step); reservoir = float64[2], ke_io = float64[1], both
+        updated in place.  Returns (alpha, energies)."""
+        en = np.zeros(3)
+        alpha = self.lib.orc_nvt_step(_d(pos), _d(vel), _d(charge), _i(image), _d(force), pos.shape[0], box[0], box[1],
+                                      box[2], L_typeid, omegac, couplstr, phmass, dt, first, n, dof, kT, tau, r_normal,
+                                      gamma_draw, _d(reservoir), _d(ke_io), _d(en))
+        return alpha, en
 
     def nve_step(self, pos, vel, charge, image, force, box, L_typeid, omegac, couplstr, phmass, dt):
         en = np.zeros(3)

@@ -176,3 +176,33 @@ def test_fkt_golden_and_long_double_truth(coracle):
         truth = coracle.rhok(frames[t], kvec)
         assert np.abs(truth - g["rho"][t]).max() <= 1e-11 * frames.shape[1]
     assert np.isclose(O.numpy_field_autocorr(g["rho"][1], g["rho"][3]), g["F"][1, 2], rtol=1e-12)
+
+
+@pytest.mark.parametrize("first,n", [(0, 500), (100, 301), (0, 0)])
+def test_nvt_harness_step_is_bussi_then_nve_then_ke(coracle, first, n):
+    """orc_nvt_step (SURVEY.md 8f.1 harness) == orc_bussi_step ; orc_nve_step ; orc_kinetic_energy, bit for
+    bit: folding the rescale into the first half step and the KE into the second changes no rounding."""
+    s = synth.make_system(500, replica=11)
+    dof, dt, r, gm = 3.0 * max(n, 1) - 3.0, synth.DT_1FS, -0.4, 700.0
+    idx = np.arange(first, first + n, dtype=np.uint32)
+    f0 = coracle.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, 0.01, 1e-3)["force"]
+    # fused
+    pa, va, fa = s.pos.copy(), s.vel.copy(), f0.copy()
+    ke = np.array([coracle.kinetic_energy(va, idx)]) if n else np.zeros(1)
+    res_a = np.zeros(2)
+    # composed
+    pb, vb, fb = s.pos.copy(), s.vel.copy(), f0.copy()
+    res_b = np.zeros(2)
+    for _ in range(5):
+        alpha_a, en_a = coracle.nvt_step(pa, va, s.charge, s.image, fa, s.box, s.L_typeid, 0.01, 1e-3, 1.0, dt, first, n,
+                                         dof, synth.KT_100K, synth.TAU_5PS, r, gm, res_a, ke)
+        if n and dof != 0.0:
+            alpha_b, _ = coracle.bussi_step(vb, idx, dof, dt, synth.KT_100K, synth.TAU_5PS, r, gm, res_b)
+            assert alpha_a == alpha_b
+        else:
+            assert alpha_a == 1.0
+        en_b = coracle.nve_step(pb, vb, s.charge, s.image, fb, s.box, s.L_typeid, 0.01, 1e-3, 1.0, dt)
+        assert np.array_equal(pa, pb) and np.array_equal(va, vb) and np.array_equal(fa, fb)
+        assert np.array_equal(en_a, en_b) and np.array_equal(res_a, res_b)
+        if n:
+            assert ke[0] == coracle.kinetic_energy(vb, idx)
