@@ -74,6 +74,10 @@ _SIGNATURES = {
     "cavb200_net_force_add_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _u32, _dbl, _vp]),
     "cavb200_nvt_step_one_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _dbl, _u32, _dbl, _u32, _u32, _BP, _vp]),
     "cavb200_nvt_step_two_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _dbl, _u32, _dbl, _u32, _u32, _vp]),
+    "cavb200_track_open": (C.c_int, [_vp, _u32]),
+    "cavb200_track_set_reference": (C.c_int, [_vp, _vp]),
+    "cavb200_track_record": (C.c_int, [_vp, _u64, _vp, _u32, _vp]),
+    "cavb200_track_read": (C.c_int, [_vp, _dp, _u32, C.POINTER(_u32), C.POINTER(_u64), _vp]),
     "cavb200_rhok": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _u32, _vp, _u32, _vp, _vp]),
     "cavb200_fkt": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp]),
     "cavb200_shard_nccl_unique_id": (C.c_int, [_vp]),
@@ -414,6 +418,27 @@ class Handle:
         check(self.lib.cavb200_nvt_step_two_rank1(self.h, _ptr(vel), _ptr(force_other), _ptr(charge), _ptr(pos), N, dt,
                                                   L_typeid & 0xFFFFFFFF, couplstr, group_first, n_group, stream),
               "cavb200_nvt_step_two_rank1")
+
+    # -- device-side trackers --------------------------------------------------
+    TRACK_FIELDS = ("timestep", "dx", "dy", "dz", "qx", "qy", "qz", "harmonic", "coupling", "dipole_self", "autocorr",
+                    "cavity_ke", "group_ke", "alpha", "reservoir", "photon_idx")
+
+    def track_open(self, capacity: int):
+        check(self.lib.cavb200_track_open(self.h, capacity), "cavb200_track_open")
+
+    def track_set_reference(self, stream=None):
+        check(self.lib.cavb200_track_set_reference(self.h, stream), "cavb200_track_set_reference")
+
+    def track_record(self, timestep: int, vel, N: int, stream=None):
+        check(self.lib.cavb200_track_record(self.h, timestep, _ptr(vel), N, stream), "cavb200_track_record")
+
+    def track_read(self, max_records: int, stream=None):
+        """-> (records float64[n, 16] oldest first, total appended since open)"""
+        out = np.zeros((max(max_records, 1), 16), dtype=np.float64)
+        n, total = C.c_uint32(0), C.c_uint64(0)
+        check(self.lib.cavb200_track_read(self.h, out.ctypes.data_as(_dp), max_records, C.byref(n), C.byref(total), stream),
+              "cavb200_track_read")
+        return out[:n.value], int(total.value)
 
     def nve_half_kick(self, vel, force, N, dt, stream=None):
         check(self.lib.cavb200_nve_half_kick(self.h, _ptr(vel), _ptr(force), N, dt, stream), "cavb200_nve_half_kick")

@@ -150,6 +150,7 @@ int cavb200_destroy(cavb200_handle* h)
     cudaSetDevice(h->device);
     cavb_shard_release(h);
     cavb_host_release(h);
+    cavb_track_release(h);
     cudaFree(h->partials);
     cudaFree(h->scalars);
     cudaFree(h->counters);

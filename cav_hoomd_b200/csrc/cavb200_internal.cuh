@@ -121,6 +121,9 @@ struct cavb200_handle
     int slot_used[CAVB_HOST_SLOTS];
     cavb::Scalars* slot_scalars;      // device, one per slot
     cavb::Scalars* slot_scalars_host; // pinned, one per slot
+    // device-side tracker ring (track.cu): records | reference dipole | counter
+    double* track_ring;
+    uint64_t track_capacity;
     // F(k,t) workspace
     double* rhok_partials;
     uint64_t rhok_partials_bytes;
@@ -237,6 +240,7 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xo
 // teardown hooks of the sharded and host-buffer paths (shard.cu, host.cu)
 void cavb_shard_release(cavb200_handle* h);
 void cavb_host_release(cavb200_handle* h);
+void cavb_track_release(cavb200_handle* h);
 
 // launch helpers implemented in the .cu files
 namespace cavb

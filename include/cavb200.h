@@ -190,6 +190,30 @@ int cavb200_nvt_step_two_rank1(cavb200_handle* h, double* vel, const double* for
                                const double* pos, uint32_t N, double dt, uint32_t L_typeid, double couplstr,
                                uint32_t group_first, uint32_t n_group, void* stream);
 
+/* ---- device-side trackers ------------------------------------------------------
+ * Replace the per-step cpu_local_snapshot of the reference's trackers (reference
+ * src/cavitymd/analysis.py:188,234 AutocorrelationTracker / DipoleAutocorrelation, :1327
+ * CavityModeTracker, :535,578 EnergyTracker) by a 128-byte record per step, appended on the device from
+ * the results the last cavb200_force* / cavb200_bussi* / nvt step left there; the host reads the ring
+ * once per output period.  Record layout (CAVB200_TRACK_WORDS doubles):
+ *   [0] timestep   [1..3] total dipole d = sum_i q_i r~_i (compute_total_dipole_moment, :18-31; the photon
+ *   is excluded, which is the same number whenever its charge is 0, examples/05_advanced_run.py:502)
+ *   [4..6] photon coordinate q (unwrapped)   [7..9] harmonic, coupling, dipole-self energy
+ *   [10] C(t) = d(ref) . d(t) (:222-224)   [11] cavity-mode kinetic energy 1/2 m|v|^2 of the photon (:1352-1354;
+ *   0 if vel == NULL or there is no photon)   [12] group kinetic energy   [13] alpha   [14] cumulative
+ *   reservoir energy   [15] photon index (-1: none).
+ *   cavb200_track_open(capacity)   allocate / reset the ring (oldest records are overwritten when full)
+ *   cavb200_track_set_reference    d(ref) <- current dipole (_initialize_reference / _start_new_reference)
+ *   cavb200_track_record           append one record; asynchronous, stream-ordered after the step's kernels
+ *   cavb200_track_read             newest min(max_records, stored) records, oldest first; *total = records
+ *                                  appended since open.  Synchronises the stream. */
+#define CAVB200_TRACK_WORDS 16
+int cavb200_track_open(cavb200_handle* h, uint32_t capacity);
+int cavb200_track_set_reference(cavb200_handle* h, void* stream);
+int cavb200_track_record(cavb200_handle* h, uint64_t timestep, const double* vel, uint32_t N, void* stream);
+int cavb200_track_read(cavb200_handle* h, double* out, uint32_t max_records, uint32_t* n_out, uint64_t* total,
+                       void* stream);
+
 /* ---- F(k,t): density field --------------------------------------------------------------------
  * rho[t][k] = sum_j exp(i kvec[k] . r_j(t)) over ALL N particles of frame t (wrapped positions),
  * the batched form of compute_density_field (reference src/cavitymd/analysis.py:34-47).

@@ -211,6 +211,50 @@ def test_step_host_buffers(handle, coracle):
         assert bo["err"] == 0.0
 
 
+def test_step_host_pipelined_slots(handle, coracle):
+    """cavb200_step_host_submit / _wait: several independent host-resident systems of DIFFERENT sizes in flight
+    at once (next upload under this download); every slot returns its own system's forces, velocities,
+    energies and alpha (the per-handle Scalars block is snapshotted per slot), and slots are reusable."""
+    p = capi.Params.make(0.01, 1e-3)
+    sizes = [60000, 1000, 33, 150000, 60001, 7, 20000]
+    systems, refs = [], []
+    for r, n_mol in enumerate(sizes):
+        s = synth.make_system(n_mol, replica=r)
+        a = bargs(max(3.0 * n_mol - 3.0, 1.0))
+        ref = coracle.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, 0.01, 1e-3)
+        vref = s.vel.copy()
+        alpha, ke = coracle.bussi_step(vref, np.arange(n_mol, dtype=np.uint32), a.dof, DT, KT, TAU, a.r_normal,
+                                       a.gamma_draw, np.zeros(2))
+        bufs = {k: capi.PinnedArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+        bufs["force"] = capi.PinnedArray((s.N, 4), np.float64)
+        bufs["force"].array[:] = np.nan
+        systems.append((s, a, bufs))
+        refs.append((ref, vref, alpha, ke))
+    handle.bussi_reset()
+    SLOTS = 3
+
+    def submit(k):
+        s, a, b = systems[k]
+        handle.step_host_submit(k % SLOTS, b["pos"], b["charge"], b["image"], b["force"], b["vel"], s.N, s.box, s.L_typeid,
+                                p, 0, s.N - 1, a)
+
+    for k in range(SLOTS - 1):
+        submit(k)
+    for k in range(len(sizes)):
+        if k + SLOTS - 1 < len(sizes):
+            submit(k + SLOTS - 1)
+        en, bo = handle.step_host_wait(k % SLOTS)
+        s, a, b = systems[k]
+        ref, vref, alpha, ke = refs[k]
+        assert np.abs(b["force"].array - ref["force"]).max() <= 1e-10 * np.abs(ref["force"]).max()
+        assert np.allclose(b["vel"].array, vref, rtol=1e-12, atol=0)
+        assert np.allclose(en, ref["energies"], rtol=1e-10)
+        assert abs(bo["alpha"] - alpha) <= 1e-12 * abs(alpha) and abs(bo["ke"] - ke) <= 1e-12 * ke
+        assert bo["err"] == 0.0
+    with pytest.raises(capi.CavbError):
+        handle.step_host_wait(99)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("n,first,use_list", [(1, 0, False), (33, 0, False), (1000, 7, False), (262145, 0, False),
                                                (50001, 0, True), (0, 0, False)])
