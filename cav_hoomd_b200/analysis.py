@@ -96,3 +96,123 @@ class FieldAutocorrelationTracker:
             self._add_reference(timestep)
             self.last_reference_step = timestep
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# device-side scalar trackers
+# ---------------------------------------------------------------------------------------------
+KB_HARTREE_PER_K = 3.167e-6  # reference src/cavitymd/utils.py:13
+
+
+class StepRecorder:
+    """One 128-byte record per step, appended on the device (cavb200_track_record) from what the force and
+    thermostat kernels left there.  The reference's trackers take sim.state.cpu_local_snapshot every step
+    (analysis.py:188,234,1327) for the same scalars; here nothing leaves the device until `read`."""
+
+    def __init__(self, state, handle: capi.Handle, capacity: int = 16384):
+        self.state, self.handle, self.capacity = state, handle, capacity
+        handle.track_open(capacity)
+        self._seen = 0
+
+    def set_reference(self, stream=None):
+        self.handle.track_set_reference(stream)
+
+    def act(self, timestep: int, stream=None):
+        self.handle.track_record(timestep, self.state.vel, self.state.N, stream)
+
+    def read(self, stream=None):
+        """Records appended since the previous read, oldest first (float64[n, 16]; capi.Handle.TRACK_FIELDS)."""
+        _, total = self.handle.track_read(0, stream)
+        new = min(total - self._seen, self.capacity)
+        rec, total = self.handle.track_read(new, stream)
+        self._seen = total
+        return rec
+
+
+class DipoleAutocorrelation:
+    """C(t) = d(ref) . d(t) (AutocorrelationTracker('dipole'), reference analysis.py:152-258,1424-1446): a new
+    reference when an output lands on a multiple of 10000 steps (:247-249); same text format (:192-197,240-242)."""
+
+    def __init__(self, recorder: StepRecorder, dt: float, output_prefix="dipole_autocorr", output_period_steps=1000,
+                 write_files=True):
+        self.rec, self.dt = recorder, dt
+        self.output_prefix, self.output_period_steps, self.write_files = output_prefix, output_period_steps, write_files
+        self.output_file_number = 0
+        self.last_output_step = 0
+        self.current_autocorr_value = None
+        self.series = []  # (reference number, timestep, C)
+        recorder.set_reference()
+        recorder.act(0)
+        r = recorder.read()[-1]
+        self.current_autocorr_value = float(r[10])
+        self._header(0, r[10])
+
+    def _path(self):
+        return f"{self.output_prefix}_{self.output_file_number}.txt"
+
+    def _time_ps(self, timestep):
+        return self.dt * timestep * 2.418884e-5  # PhysicalConstants.TIME_PS_CONVERSION (reference utils.py:18)
+
+    def _header(self, timestep, c0):
+        self.series.append((self.output_file_number, int(timestep), float(c0)))
+        if not self.write_files:
+            return
+        with open(self._path(), "w") as f:
+            f.write("# Dipole autocorrelation data\n")
+            f.write(f"# Reference number: {self.output_file_number}\n")
+            f.write(f"# Output period: {self.output_period_steps} steps\n")
+            f.write("# timestep t(ps) C(t)\n")
+            f.write(f"{int(timestep)} {self._time_ps(timestep):.6f} {c0:.6f}\n")
+
+    def act(self, timestep: int, stream=None):
+        """Per step: one asynchronous device record.  Only an output step reads anything back."""
+        if timestep == 0:
+            return
+        self.rec.act(timestep, stream)
+        if timestep - self.last_output_step >= self.output_period_steps:
+            r = self.rec.read(stream)[-1]
+            self.current_autocorr_value = float(r[10])
+            self.series.append((self.output_file_number, timestep, float(r[10])))
+            if self.write_files:
+                with open(self._path(), "a") as f:
+                    f.write(f"{timestep} {self._time_ps(timestep):.6f} {r[10]:.6f}\n")
+            self.last_output_step = timestep
+            if timestep % 10000 == 0:
+                self.output_file_number += 1
+                self.rec.set_reference(stream)
+                self._header(timestep, float(np.dot(r[1:4], r[1:4])))
+
+    @property
+    def current_autocorr(self):
+        return self.current_autocorr_value if self.current_autocorr_value is not None else 0.0
+
+
+class CavityModeTracker:
+    """Cavity-mode kinetic / harmonic / total energy and temperature (reference analysis.py:1285-1417) from
+    the newest device record instead of a snapshot."""
+
+    def __init__(self, recorder: StepRecorder):
+        self.rec = recorder
+        self._last = np.zeros(16)
+
+    def refresh(self, stream=None):
+        r, _ = self.rec.handle.track_read(1, stream)
+        if len(r):
+            self._last = r[-1]
+        return self
+
+    @property
+    def cavity_kinetic_energy(self):
+        return float(self._last[11])
+
+    @property
+    def cavity_potential_energy_harmonic(self):
+        return float(self._last[7])
+
+    @property
+    def cavity_total_energy(self):
+        return float(self._last[11] + self._last[7])
+
+    @property
+    def cavity_temperature(self):
+        return (2.0 / 3.0) * float(self._last[11]) / KB_HARTREE_PER_K  # :1367

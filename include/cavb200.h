@@ -201,7 +201,8 @@ int cavb200_nvt_step_two_rank1(cavb200_handle* h, double* vel, const double* for
  *   [4..6] photon coordinate q (unwrapped)   [7..9] harmonic, coupling, dipole-self energy
  *   [10] C(t) = d(ref) . d(t) (:222-224)   [11] cavity-mode kinetic energy 1/2 m|v|^2 of the photon (:1352-1354;
  *   0 if vel == NULL or there is no photon)   [12] group kinetic energy   [13] alpha   [14] cumulative
- *   reservoir energy   [15] photon index (-1: none).
+ *   reservoir energy   [15] photon index (-1: none; the cavity force then computes nothing, reference
+ *   src/CavityForceCompute.cc:149-156, and [1..11] are 0).
  *   cavb200_track_open(capacity)   allocate / reset the ring (oldest records are overwritten when full)
  *   cavb200_track_set_reference    d(ref) <- current dipole (_initialize_reference / _start_new_reference)
  *   cavb200_track_record           append one record; asynchronous, stream-ordered after the step's kernels

@@ -268,3 +268,20 @@ def numpy_density_field(positions, wavevectors):
 def numpy_field_autocorr(field0, field_t):
     """src/cavitymd/analysis.py:359-364."""
     return np.mean(np.real(field0 * np.conj(field_t)))
+
+
+def numpy_total_dipole(position, image, charge, box_lengths):
+    """compute_total_dipole_moment (reference src/cavitymd/analysis.py:18-31): np.dot(charge, unwrapped)."""
+    return np.dot(charge, numpy_unwrap(position, image, box_lengths))
+
+
+def numpy_cavity_mode(position, image, velocity, mass, typeid, box_lengths, harmonic_energy, kb=3.167e-6):
+    """CavityModeTracker.compute_cavity_properties (reference src/cavitymd/analysis.py:1324-1371):
+    -> (kinetic, potential, total, temperature) of the first typeid == 2 particle, zeros if none."""
+    mask = typeid == 2
+    if not np.any(mask):
+        return 0.0, 0.0, 0.0, 0.0
+    m = mass[mask][0]
+    v = velocity[mask][0]
+    ke = 0.5 * m * np.sum(v ** 2)
+    return ke, harmonic_energy, ke + harmonic_energy, (2.0 / 3.0) * ke / kb
