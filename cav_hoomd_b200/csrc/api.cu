@@ -130,7 +130,7 @@ int cavb200_create(cavb200_handle** out, int device)
         cavb200_destroy(h);
         return (int)e;
         }
-    h->tune.variant = 2; // split-phase step kernel; force-only / Bussi-only calls use the fused kernel (variant 1)
+    h->tune.variant = 3; // split-phase step kernel with a folder CTA; force-only / Bussi-only calls use the fused kernel (variant 1)
     h->tune.threads = 384;
     h->tune.ctas_per_sm = 2;
     h->tune.unroll = 2;

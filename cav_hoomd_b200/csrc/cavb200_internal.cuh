@@ -74,7 +74,7 @@ struct __align__(16) Scalars
 
 struct Tuning
     {
-    int variant;         // 0 = reduce kernel + apply kernel, 1 = fused persistent kernel, 2 = split-phase step kernel (default)
+    int variant;         // 0 = reduce kernel + apply kernel, 1 = fused persistent kernel, 2 = split-phase step kernel, 3 = split-phase with a folder CTA (default)
     int threads;         // CTA size of the streaming kernels (256 / 512 / 1024)
     int ctas_per_sm;     // resident CTAs per SM the grid is sized for
     int unroll;          // independent particle loads in flight per thread (1, 2 or 4)

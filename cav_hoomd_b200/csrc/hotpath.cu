@@ -152,6 +152,122 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         my_stamps[6] = globaltimer_ns();
     }
 
+// variant 3 ("split-phase with a folder CTA"): the split-phase schedule, but ONE extra CTA that streams
+// nothing folds the per-CTA records (it waits for them, so it runs behind the stragglers by itself) and
+// publishes the Final record; the streaming CTAs only poll that record.  In k_split every CTA spends
+// 2.75 + 2.0 us per step folding all records (profiles/split_r1e.txt); here that is two L2 round trips.
+//     streaming CTA:  dipole reduce -> publish | KE reduce -> publish | take Dq -> forces | take alpha -> rescale
+//     folder CTA:     fold dipole records -> publish Final(F) | fold KE records -> publish Final(K)
+// The dipole is the correctly rounded sum of the same terms as in the other variants, folded over one
+// record fewer (grid - 1 streaming CTAs): results agree to the last bit or two, not bit for bit.
+template<int UNROLL, int LB>
+__global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
+    k_split_folder(ForceIn f, BussiIn b, Partial* recsF, Partial* recsB, Partial* finals, Scalars* scalars,
+                   unsigned long long* epoch_ctr, unsigned long long* stamps)
+    {
+    __shared__ BlockScratch sc;
+    unsigned long long* my_stamps = (stamps && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
+    if (my_stamps)
+        my_stamps[0] = globaltimer_ns();
+    pdl_wait();
+    if (threadIdx.x == 0)
+        {
+        sc.flags = 0u;
+        sc.epoch = ld_relaxed_u64(epoch_ctr) + 1ull;
+        }
+    StreamGrid g;
+    g.nblk = gridDim.x - 1;
+    g.blk = blockIdx.x - 1; // CTA 0 is the folder: it is resident first, long before it is needed
+    if (blockIdx.x == 0)
+        {
+        // ---- folder ----
+        // The fold runs ONCE per launch, on one SM, while the rest of the grid streams: its instructions
+        // are cold (evicted from L2 by the 148 MB a step moves) and every instruction-cache miss costs a
+        // loaded memory round trip -- measured: 6 us for a fold that takes 2.75 us hot.  So the folder
+        // first runs the very same code (same loop body, pass 0) over a bank of dummy records it wrote
+        // itself, while it has nothing to do anyway, and then (pass 1) over the real records.
+        __syncthreads();
+        const unsigned long long epoch = sc.epoch, dummy_epoch = ~epoch;
+        Partial* dummy = recsF + MAX_PARTIALS / 4; // unused part of the force bank (grid <= MAX_PARTIALS / 4)
+        for (int j = threadIdx.x; j < (int)g.nblk; j += blockDim.x)
+            {
+            Partial z = {};
+            z.first_L = ~0ull;
+            z.ke = 1.0;
+            if (j == 0)
+                z.first_L = 0ull; // one candidate, so that the photon path is warmed up too
+            publish_record(dummy + j, z, dummy_epoch);
+            }
+        __syncthreads();
+        bool timeout_f = false;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++)
+            {
+            const bool real = pass == 1;
+            const unsigned long long ep = real ? epoch : dummy_epoch;
+            if (my_stamps && real)
+                my_stamps[1] = globaltimer_ns();
+            combine_phase<true, false, true, true>(real ? recsF : dummy, (int)g.nblk, ep, f, b, sc, scalars, real,
+                                                   (my_stamps && real) ? my_stamps + 8 * 1024 : nullptr);
+            if (threadIdx.x == 0)
+                publish_final<true>(real ? finals + 0 : dummy + g.nblk, sc.fin, ep);
+            if (my_stamps && real)
+                my_stamps[3] = globaltimer_ns();
+            timeout_f = sc.fin.timeout != 0;
+            __syncthreads();
+            combine_phase<false, true, true, true>(real ? recsB : dummy, (int)g.nblk, ep, f, b, sc, scalars, real);
+            if (threadIdx.x == 0)
+                {
+                if (timeout_f)
+                    sc.fin.timeout = 1;
+                publish_final<false>(real ? finals + 1 : dummy + g.nblk + 1, sc.fin, ep);
+                if (real)
+                    *epoch_ctr = epoch; // every streaming CTA has published twice, hence read the counter
+                }
+            __syncthreads();
+            }
+        if (my_stamps)
+            my_stamps[5] = globaltimer_ns();
+        pdl_launch_dependents();
+        return;
+        }
+    // ---- streaming CTAs ----
+    reduce_phase<true, false, UNROLL>(f, b, sc, g);
+    const unsigned long long epoch = sc.epoch;
+    if (threadIdx.x == 0)
+        publish_record(recsF + g.blk, sc.rec, epoch);
+    if (my_stamps)
+        my_stamps[1] = globaltimer_ns();
+    FinalSectors pre;
+        {
+        Acc a;
+        reduce_loops<false, true, UNROLL>(a, f, b, g);
+        // Final(F) has normally been out since the middle of this pass: fetch it under the merge tree
+        pre = prefetch_final<true>(finals + 0);
+        block_merge<false, true>(a, f, sc);
+        }
+    if (threadIdx.x == 0)
+        publish_record(recsB + g.blk, sc.rec, epoch);
+    if (my_stamps)
+        my_stamps[2] = globaltimer_ns();
+    const Final finF = take_final<true>(finals + 0, epoch, pre);
+    if (my_stamps)
+        my_stamps[3] = globaltimer_ns();
+    if (!finF.timeout)
+        apply_phase<true, false, UNROLL>(finF, f, b, g);
+    if (my_stamps)
+        my_stamps[4] = globaltimer_ns();
+    const Final finK = take_final<false>(finals + 1, epoch, prefetch_final<false>(finals + 1));
+    if (my_stamps)
+        my_stamps[5] = globaltimer_ns();
+    if (finF.timeout || finK.timeout)
+        return;
+    pdl_launch_dependents();
+    apply_phase<false, true, UNROLL>(finK, f, b, g);
+    if (my_stamps)
+        my_stamps[6] = globaltimer_ns();
+    }
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -172,25 +288,37 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         max_grid = MAX_PARTIALS;
     Final* fin_dev = reinterpret_cast<Final*>(h->counters + 8);
 
-    if (FORCE && BUSSI && h->tune.variant == 2 && h->coop_supported && b.rescale)
+    if (FORCE && BUSSI && (h->tune.variant == 2 || h->tune.variant == 3) && h->coop_supported && b.rescale)
         {
+        const bool folder = h->tune.variant == 3;
+        const void* kern = folder ? (const void*)k_split_folder<UNROLL, LB> : (const void*)k_split<UNROLL, LB>;
         int per_sm = 0;
-        CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split<UNROLL, LB>, threads, 0));
+        if (folder)
+            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split_folder<UNROLL, LB>, threads, 0));
+        else
+            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split<UNROLL, LB>, threads, 0));
         if (per_sm < 1)
             return (int)cudaErrorLaunchOutOfResources;
         if (max_grid > per_sm * h->num_sms)
             max_grid = per_sm * h->num_sms;
-        if (max_grid > MAX_PARTIALS / 2)
-            max_grid = MAX_PARTIALS / 2;
-        const int grid = (int)(want < (unsigned long long)max_grid ? want : (unsigned long long)max_grid);
+        if (max_grid > MAX_PARTIALS / 4 - 2)
+            max_grid = MAX_PARTIALS / 4 - 2;
+        int grid = (int)(want < (unsigned long long)max_grid ? want : (unsigned long long)max_grid);
+        if (folder) // one CTA of the co-resident grid folds instead of streaming
+            grid = (grid < max_grid ? grid : max_grid - 1) + 1;
+        if (grid < (folder ? 2 : 1))
+            return (int)cudaErrorLaunchOutOfResources;
         Partial* recsF = h->partials;
         Partial* recsB = h->partials + MAX_PARTIALS / 2;
+        Partial* finals = h->partials + MAX_PARTIALS - 2; // the last two records of the thermostat half's bank
         Scalars* sca = h->scalars;
         unsigned long long* arr = h->counters + 2;
         ForceIn ff = f;
         BussiIn bb = b;
         unsigned long long* stamps = h->tune.stamps ? h->stamps : nullptr;
-        void* args[] = {&ff, &bb, &recsF, &recsB, &sca, &arr, &stamps};
+        void* args_split[] = {&ff, &bb, &recsF, &recsB, &sca, &arr, &stamps};
+        void* args_folder[] = {&ff, &bb, &recsF, &recsB, &finals, &sca, &arr, &stamps};
+        void** args = folder ? args_folder : args_split;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(threads);
@@ -208,7 +336,7 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
             }
         cfg.attrs = attrs;
         cfg.numAttrs = 1;
-        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_split<UNROLL, LB>, args));
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, kern, args));
         h->launches += 1;
         return 0;
         }

@@ -179,10 +179,24 @@ __device__ __forceinline__ void take_particle(Acc& a, unsigned int i, const doub
         }
     }
 
-template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const BussiIn& b)
+// Which CTAs stream particles: all of the grid (default), or a sub-range when some CTAs have another
+// role (the folder CTA of k_split_folder).
+struct StreamGrid
     {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int nblk, blk;
+    };
+__device__ __forceinline__ StreamGrid whole_grid()
+    {
+    StreamGrid g;
+    g.nblk = gridDim.x;
+    g.blk = blockIdx.x;
+    return g;
+    }
+
+template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const BussiIn& b, const StreamGrid g = whole_grid())
+    {
+    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
+    unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     const unsigned long long n = b.n;
     double ke[UNROLL > 1 ? UNROLL : 1];
 #pragma unroll
@@ -224,14 +238,14 @@ template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const Bus
 // Separate force and KE loops (the first version) paid the memory ramp twice.  A software-pipelined
 // variant with predicated loads was slower than this plain "U loads, U consumes" loop and was dropped.
 template<bool FORCE, bool KE, int U>
-__device__ __forceinline__ void reduce_stream(Acc& a, const ForceIn& f, const BussiIn& b)
+__device__ __forceinline__ void reduce_stream(Acc& a, const ForceIn& f, const BussiIn& b, const StreamGrid g = whole_grid())
     {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
     const unsigned long long nf = FORCE ? (unsigned long long)f.N : 0ull;
     const unsigned long long nk = KE ? (unsigned long long)b.n : 0ull; // group = [0, n)
     const unsigned long long common = (FORCE && KE) ? (nf < nk ? nf : nk) : (FORCE ? nf : nk);
     const unsigned long long all = nf > nk ? nf : nk;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long i = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     double ke[U];
 #pragma unroll
     for (int k = 0; k < U; k++)
@@ -364,20 +378,27 @@ __device__ __forceinline__ void block_merge(Acc& a, const ForceIn& f, BlockScrat
     }
 
 template<bool FORCE, bool BUSSI, int UNROLL>
-__device__ __forceinline__ void reduce_phase(const ForceIn& f, const BussiIn& b, BlockScratch& sc)
+__device__ __forceinline__ void reduce_loops(Acc& a, const ForceIn& f, const BussiIn& b, const StreamGrid g = whole_grid())
     {
-    Acc a;
     acc_zero(a);
     if (BUSSI && (b.gidx != nullptr || b.first != 0))
         {
         // index-list group or a group that does not start at particle 0: the velocity pass cannot
         // share the particle loop
         if (FORCE)
-            reduce_stream<true, false, UNROLL>(a, f, b);
-        reduce_ke<UNROLL>(a, b);
+            reduce_stream<true, false, UNROLL>(a, f, b, g);
+        reduce_ke<UNROLL>(a, b, g);
         }
     else
-        reduce_stream<FORCE, BUSSI, UNROLL>(a, f, b);
+        reduce_stream<FORCE, BUSSI, UNROLL>(a, f, b, g);
+    }
+
+template<bool FORCE, bool BUSSI, int UNROLL>
+__device__ __forceinline__ void reduce_phase(const ForceIn& f, const BussiIn& b, BlockScratch& sc,
+                                             const StreamGrid g = whole_grid())
+    {
+    Acc a;
+    reduce_loops<FORCE, BUSSI, UNROLL>(a, f, b, g);
     block_merge<FORCE, BUSSI>(a, f, sc);
     }
 
@@ -496,26 +517,49 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
         unsigned long long mykey = ~0ull;
         unsigned int mycnt = 0, mymulti = 0;
         int myrec = -1;
+        double4 mys3 = make_double4(0.0, 0.0, 0.0, 0.0);
         for (int j = tid; j < G; j += blockDim.x)
             {
             const double4* p = reinterpret_cast<const double4*>(recs + j);
             // issue all sector reads before looking at any of them
-            double4 s2 = ld_rec<SYS>(p + 2), s0, s1;
+            double4 s2 = ld_rec<SYS>(p + 2), s0, s1, s3;
             if (FORCE)
                 {
                 s0 = ld_rec<SYS>(p + 0);
                 s1 = ld_rec<SYS>(p + 1);
+                // the photon's position travels with the other sectors: the one lane that turns out to
+                // hold the candidate then has it without a second, dependent L2 round trip
+                s3 = ld_rec<SYS>(p + 3);
                 }
             if (WAIT)
                 {
-                if (!sector_ok(s2, epoch))
-                    s2 = read_sector<true, SYS>(p + 2, epoch, late);
+                // poll ALL the sectors this thread needs with one round trip per attempt (checking them one
+                // after the other costs a dependent L2 round trip each -- 1-2 us apiece while the grid streams)
+                bool ok = sector_ok(s2, epoch);
                 if (FORCE)
+                    ok = ok && sector_ok(s0, epoch) && sector_ok(s1, epoch) && sector_ok(s3, epoch);
+                if (!ok)
                     {
-                    if (!sector_ok(s0, epoch))
-                        s0 = read_sector<true, SYS>(p + 0, epoch, late);
-                    if (!sector_ok(s1, epoch))
-                        s1 = read_sector<true, SYS>(p + 1, epoch, late);
+                    const unsigned long long t0 = globaltimer_ns();
+                    do
+                        {
+                        __nanosleep(32);
+                        s2 = ld_rec<SYS>(p + 2);
+                        if (FORCE)
+                            {
+                            s0 = ld_rec<SYS>(p + 0);
+                            s1 = ld_rec<SYS>(p + 1);
+                            s3 = ld_rec<SYS>(p + 3);
+                            }
+                        ok = sector_ok(s2, epoch);
+                        if (FORCE)
+                            ok = ok && sector_ok(s0, epoch) && sector_ok(s1, epoch) && sector_ok(s3, epoch);
+                        if (!ok && globaltimer_ns() - t0 > (SYS ? PEER_TIMEOUT_NS : HANDOFF_TIMEOUT_NS))
+                            {
+                            late = true; // never hang the GPU
+                            break;
+                            }
+                        } while (!ok);
                     }
                 }
             if (FORCE)
@@ -533,6 +577,7 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
                         {
                         mykey = idx;
                         myrec = j;
+                        mys3 = s3;
                         }
                     }
                 }
@@ -551,7 +596,9 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
             const bool i_hold = (wmin != ~0ull) && (mykey == wmin);
             if (i_hold)
                 {
-                s3 = read_sector<WAIT, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 3, epoch, late);
+                s3 = mys3;
+                if (WAIT && !sector_ok(s3, epoch))
+                    s3 = read_sector<true, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 3, epoch, late);
                 if (!FINALIZE) // a rank-level merge may lose the global vote later: keep the term too
                     s4 = read_sector<WAIT, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 4, epoch, late);
                 }
@@ -783,10 +830,11 @@ __device__ __forceinline__ double4 force_of(unsigned long long i, double c, cons
     return o;
     }
 
-template<int UNROLL> __device__ __forceinline__ void apply_force(const Final& fin, const ForceIn& f)
+template<int UNROLL>
+__device__ __forceinline__ void apply_force(const Final& fin, const ForceIn& f, const StreamGrid g = whole_grid())
     {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
+    unsigned long long i = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     const unsigned long long N = f.N;
     if (UNROLL > 1)
         {
@@ -805,10 +853,11 @@ template<int UNROLL> __device__ __forceinline__ void apply_force(const Final& fi
         st256(f.force + i, force_of(i, __ldg(f.charge + i), fin, f));
     }
 
-template<int UNROLL> __device__ __forceinline__ void apply_rescale(double alpha, const BussiIn& b)
+template<int UNROLL>
+__device__ __forceinline__ void apply_rescale(double alpha, const BussiIn& b, const StreamGrid g = whole_grid())
     {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
+    unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     const unsigned long long n = b.n;
     if (UNROLL > 1)
         {
@@ -846,15 +895,16 @@ template<int UNROLL> __device__ __forceinline__ void apply_rescale(double alpha,
 
 // fused apply for a group [0, n): charge and velocity loads of U particles first, then the stores
 template<bool FORCE, bool RESCALE, int U>
-__device__ __forceinline__ void apply_stream(const Final& fin, const ForceIn& f, const BussiIn& b)
+__device__ __forceinline__ void apply_stream(const Final& fin, const ForceIn& f, const BussiIn& b,
+                                             const StreamGrid g = whole_grid())
     {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
     const unsigned long long nf = FORCE ? (unsigned long long)f.N : 0ull;
     const unsigned long long nk = RESCALE ? (unsigned long long)b.n : 0ull;
     const unsigned long long common = (FORCE && RESCALE) ? (nf < nk ? nf : nk) : (FORCE ? nf : nk);
     const unsigned long long all = nf > nk ? nf : nk;
     const double alpha = fin.alpha;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long i = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     for (; i + (U - 1) * stride < common; i += U * stride)
         {
         double c[FORCE ? U : 1];
@@ -898,17 +948,95 @@ __device__ __forceinline__ void apply_stream(const Final& fin, const ForceIn& f,
     }
 
 template<bool FORCE, bool BUSSI, int UNROLL>
-__device__ __forceinline__ void apply_phase(const Final& fin, const ForceIn& f, const BussiIn& b)
+__device__ __forceinline__ void apply_phase(const Final& fin, const ForceIn& f, const BussiIn& b,
+                                            const StreamGrid g = whole_grid())
     {
     const bool rescale = BUSSI && b.rescale && fin.bussi_ok && fin.alpha != 1.0;
     if (BUSSI && rescale && b.gidx == nullptr && b.first == 0)
-        apply_stream<FORCE, true, UNROLL>(fin, f, b);
+        apply_stream<FORCE, true, UNROLL>(fin, f, b, g);
     else
         {
         if (FORCE)
-            apply_stream<true, false, UNROLL>(fin, f, b);
+            apply_stream<true, false, UNROLL>(fin, f, b, g);
         if (BUSSI && rescale)
-            apply_rescale<UNROLL>(fin.alpha, b);
+            apply_rescale<UNROLL>(fin.alpha, b, g);
         }
+    }
+
+// ---- Final record hand-off (k_split_folder) -----------------------------------------------------
+// The folder CTA publishes what finalize() formed in the sector format of the reduce records
+// (payload x3 + check word, one STG.256 each); every thread of a streaming CTA polls the sectors it
+// needs (the loads of a warp coalesce into one request) -- no block barrier, no shared memory.
+//   force half:      sector 0 {Dq.x, Dq.y, FL.x}   sector 1 {FL.y, FL.z, -}   sector 2 {photon_local, flags, -}
+//   thermostat half: sector 2 {alpha, flags, -}
+// flags: bit 0 many_L, bit 1 has_photon, bit 2 bussi_ok, bit 3 timeout
+__device__ __forceinline__ unsigned long long final_flags(const Final& fin)
+    {
+    return (fin.many_L ? 1ull : 0ull) | (fin.has_photon ? 2ull : 0ull) | (fin.bussi_ok ? 4ull : 0ull)
+           | (fin.timeout ? 8ull : 0ull);
+    }
+template<bool FORCE> __device__ __forceinline__ void publish_final(Partial* dst, const Final& fin, unsigned long long epoch)
+    {
+    double4* d = reinterpret_cast<double4*>(dst);
+    if (FORCE)
+        {
+        st256(d + 0, make_sector(fin.Dq[0], fin.Dq[1], fin.FL[0], epoch));
+        st256(d + 1, make_sector(fin.FL[1], fin.FL[2], 0.0, epoch));
+        st256(d + 2, make_sector(bitsd((unsigned long long)fin.photon_local), bitsd(final_flags(fin)), 0.0, epoch));
+        }
+    else
+        st256(d + 2, make_sector(fin.alpha, bitsd(final_flags(fin)), 0.0, epoch));
+    }
+// The sector loads are issued by prefetch_final (before work that does not depend on them, so the L2
+// round trip -- 1-2 us while the grid is streaming -- overlaps it) and checked / re-polled by take_final.
+struct FinalSectors
+    {
+    double4 s0, s1, s2;
+    };
+template<bool FORCE> __device__ __forceinline__ FinalSectors prefetch_final(const Partial* src)
+    {
+    const double4* p = reinterpret_cast<const double4*>(src);
+    FinalSectors r;
+    r.s2 = ld_rec<false>(p + 2);
+    if (FORCE)
+        {
+        r.s0 = ld_rec<false>(p + 0);
+        r.s1 = ld_rec<false>(p + 1);
+        }
+    return r;
+    }
+template<bool FORCE>
+__device__ __forceinline__ Final take_final(const Partial* src, unsigned long long epoch, const FinalSectors& pre)
+    {
+    const double4* p = reinterpret_cast<const double4*>(src);
+    bool late = false;
+    Final fin;
+    fin.Dq[0] = fin.Dq[1] = fin.FL[0] = fin.FL[1] = fin.FL[2] = 0.0;
+    fin.alpha = 1.0;
+    fin.photon_local = -1;
+    double4 s0 = pre.s0, s1 = pre.s1, s2 = pre.s2;
+    if (!sector_ok(s2, epoch))
+        s2 = read_sector<true>(p + 2, epoch, late);
+    if (FORCE)
+        {
+        if (!sector_ok(s0, epoch))
+            s0 = read_sector<true>(p + 0, epoch, late);
+        if (!sector_ok(s1, epoch))
+            s1 = read_sector<true>(p + 1, epoch, late);
+        fin.Dq[0] = s0.x;
+        fin.Dq[1] = s0.y;
+        fin.FL[0] = s0.z;
+        fin.FL[1] = s1.x;
+        fin.FL[2] = s1.y;
+        fin.photon_local = (long long)dbits(s2.x);
+        }
+    else
+        fin.alpha = s2.x;
+    const unsigned long long fl = dbits(s2.y);
+    fin.many_L = (int)(fl & 1ull);
+    fin.has_photon = (int)((fl >> 1) & 1ull);
+    fin.bussi_ok = (int)((fl >> 2) & 1ull);
+    fin.timeout = (int)((fl >> 3) & 1ull) | (late ? 1 : 0);
+    return fin;
     }
     } // namespace cavb

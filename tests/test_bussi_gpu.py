@@ -122,7 +122,7 @@ def test_bussi_edge_cases(handle):
     assert handle.bussi_read()["alpha"] < 0
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("n_mol", [1000, 262145])
 def test_fused_step_equals_separate_calls(handle, coracle, n_mol, variant):
     """cavb200_step == cavb200_force followed by cavb200_bussi, and both == oracle."""
@@ -157,7 +157,7 @@ def test_fused_step_equals_separate_calls(handle, coracle, n_mol, variant):
     assert np.allclose(v_fused, vref, rtol=1e-12, atol=0)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_step_under_cuda_graph(handle, coracle, variant):
     """The step captured in a CUDA graph and replayed gives the same result as direct launches
     (the hand-off keeps no host-side state)."""
@@ -277,4 +277,4 @@ def test_bussi_ke_only(handle, n, first, use_list, variant):
     got = handle.bussi_read()["ke"]
     assert abs(got - ke) <= 1e-12 * max(ke, 1e-300)
     assert np.array_equal(d_vel.numpy().view(np.uint64), s.vel.view(np.uint64))
-    handle.set_tuning(variant=2)
+    handle.set_tuning(variant=3)

@@ -1,13 +1,15 @@
 """GPU parity of cavb200_step, the one-launch cavity force + Bussi step, for every kernel variant
 (0 = reduce kernel + apply kernel, 1 = fused persistent kernel with one hand-off, 2 = split-phase
-persistent kernel, the default) on the edge cases of the reference: photon first / middle / last /
+persistent kernel, 3 = split-phase with a folder CTA, the default) on the edge cases of the reference: photon first / middle / last /
 absent / duplicated (src/CavityForceCompute.cc:73-89,120-126,149-156), thermostat groups that are a
 prefix, a window or empty, dt = 0 (src/BussiReservoirThermostat.h:45-48), zero kinetic energy
 (:57-61), sizes below one warp, ragged sizes around the CTA size, launch shapes.
 
 Tolerances: forces / energies 1e-10 relative (BASELINE), velocities and alpha 1e-12 relative, photon
-index, zero components and untouched velocities exact; the three variants must agree BIT FOR BIT
-(same per-thread summation orders)."""
+index, zero components and untouched velocities exact; variants 0-2 must agree BIT FOR BIT (same
+per-thread summation orders); variant 3 streams with one CTA fewer, so at full grids its compensated
+dipole sum runs over a different partition of the same terms: equal to <= 1e-14 relative (measured:
+bit-identical in every case here), bit for bit whenever the grid is not full."""
 import numpy as np
 import pytest
 
@@ -16,7 +18,7 @@ from cav_hoomd_b200 import capi, synth
 pytestmark = pytest.mark.gpu
 
 KT, TAU, DT = synth.KT_100K, synth.TAU_5PS, synth.DT_1FS
-VARIANTS = [0, 1, 2]
+VARIANTS = [0, 1, 2, 3]
 
 
 def run_step(handle, s, first, n, a, omegac=0.01, g=1e-3):
@@ -63,10 +65,15 @@ def test_step_sizes_all_variants_bitwise(handle, coracle, n_mol):
         handle.set_tuning(variant=variant, threads=384, ctas_per_sm=2, unroll=2)
         outs.append(run_step(handle, s, 0, n_mol, a))
         check_against_oracle(coracle, s, 0, n_mol, a, outs[-1])
-    for o in outs[1:]:
-        assert np.array_equal(o[0].view(np.uint64), outs[0][0].view(np.uint64))
+    for variant, o in zip(VARIANTS[1:], outs[1:]):
+        if variant == 3 and n_mol + 1 > 295 * 384:
+            assert np.abs(o[0] - outs[0][0]).max() <= 1e-14 * np.abs(outs[0][0]).max()
+            assert np.allclose(o[2], outs[0][2], rtol=1e-14, atol=0)
+        else:
+            assert np.array_equal(o[0].view(np.uint64), outs[0][0].view(np.uint64))
+            assert np.array_equal(o[2], outs[0][2])
         assert np.array_equal(o[1].view(np.uint64), outs[0][1].view(np.uint64))
-        assert np.array_equal(o[2], outs[0][2]) and o[5]["alpha"] == outs[0][5]["alpha"]
+        assert o[5]["alpha"] == outs[0][5]["alpha"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -109,19 +116,21 @@ def test_step_dt_zero_and_zero_ke(handle, coracle, variant):
     handle.bussi_reset()
 
 
+@pytest.mark.parametrize("variant", [2, 3])
 @pytest.mark.parametrize("threads,ctas,unroll", [(128, 2, 2), (256, 4, 2), (384, 1, 2), (512, 1, 4), (768, 1, 2), (1024, 1, 2), (256, 1, 8)])
-def test_step_launch_shapes_split_kernel(handle, coracle, threads, ctas, unroll):
-    handle.set_tuning(variant=2, threads=threads, ctas_per_sm=ctas, unroll=unroll)
+def test_step_launch_shapes_split_kernel(handle, coracle, threads, ctas, unroll, variant):
+    handle.set_tuning(variant=variant, threads=threads, ctas_per_sm=ctas, unroll=unroll)
     s = synth.make_system(150001)
     a = args_for(150001)
     check_against_oracle(coracle, s, 0, 150001, a, run_step(handle, s, 0, 150001, a))
-    handle.set_tuning(variant=2, threads=384, ctas_per_sm=2, unroll=2)
+    handle.set_tuning(variant=3, threads=384, ctas_per_sm=2, unroll=2)
 
 
-def test_step_back_to_back_epochs(handle, coracle):
+@pytest.mark.parametrize("variant", [2, 3])
+def test_step_back_to_back_epochs(handle, coracle, variant):
     """Many launches in a row on alternating systems and grid sizes: the hand-off's epoch tagging must
     never let a record of an earlier launch pass for a current one."""
-    handle.set_tuning(variant=2, threads=384, ctas_per_sm=2, unroll=2)
+    handle.set_tuning(variant=variant, threads=384, ctas_per_sm=2, unroll=2)
     systems = [synth.make_system(n, replica=k) for k, n in enumerate((300, 70001, 5, 20000))]
     p = capi.Params.make(0.01, 1e-3)
     devs = []

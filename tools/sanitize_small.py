@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """tools/sanitize_small.py -- one small invocation of every kernel of libcavb200 (for compute-sanitizer):
-force, Bussi, step (variants 0/1/2), index-list group, sharded step (one rank), NVE kicks, rhok, fkt,
+force, Bussi, step (variants 0/1/2/3), index-list group, sharded step (one rank), NVE kicks, rhok, fkt,
 host-buffer step.  Sizes are small so the bounded hand-off spins survive the sanitizer's slowdown."""
 import os
 import sys
@@ -20,7 +20,7 @@ def main():
         a = capi.BussiArgs(synth.KT_100K, synth.TAU_5PS, synth.DT_1FS, dof, 0.3, max(dof - 1, 0) / 2)
         dev = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
         d_f = capi.DeviceArray((s.N, 4), np.float64)
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             h.set_tuning(variant=variant, threads=128, ctas_per_sm=1, unroll=2)
             h.force(dev["pos"], dev["charge"], dev["image"], d_f, s.N, s.box, s.L_typeid, p)
             h.bussi(dev["vel"], None, 0, n_mol, a)
