@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
             const unsigned long long ep = real ? epoch : dummy_epoch;
             if (my_stamps && real)
                 my_stamps[1] = globaltimer_ns();
-            combine_phase<true, false, true, true>(real ? recsF : dummy, (int)g.nblk, ep, f, b, sc, scalars, real,
+            combine_phase<true, false, true, true, false, true>(real ? recsF : dummy, (int)g.nblk, ep, f, b, sc, scalars, real,
                                                    (my_stamps && real) ? my_stamps + 8 * 1024 : nullptr);
             if (threadIdx.x == 0)
                 publish_final<true>(real ? finals + 0 : dummy + g.nblk, sc.fin, ep);
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
                 my_stamps[3] = globaltimer_ns();
             timeout_f = sc.fin.timeout != 0;
             __syncthreads();
-            combine_phase<false, true, true, true>(real ? recsB : dummy, (int)g.nblk, ep, f, b, sc, scalars, real);
+            combine_phase<false, true, true, true, false, true>(real ? recsB : dummy, (int)g.nblk, ep, f, b, sc, scalars, real);
             if (threadIdx.x == 0)
                 {
                 if (timeout_f)
@@ -290,7 +290,9 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
 
     if (FORCE && BUSSI && (h->tune.variant == 2 || h->tune.variant == 3) && h->coop_supported && b.rescale)
         {
-        const bool folder = h->tune.variant == 3;
+        // the folder pays two extra L2 round trips, which only a full streaming grid hides (65k particles:
+        // 11.95 us with the folder, 10.1 us without): small systems take the plain split-phase kernel
+        const bool folder = h->tune.variant == 3 && want >= (unsigned long long)max_grid;
         const void* kern = folder ? (const void*)k_split_folder<UNROLL, LB> : (const void*)k_split<UNROLL, LB>;
         int per_sm = 0;
         if (folder)

@@ -500,7 +500,12 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 //   * the vote for the first 'L' particle, the pair trees and the finalize need TWO block barriers;
 //   * the photon position (sector 3) is fetched by the one lane whose record holds the candidate,
 //     concurrently with the tree; sector 4 is touched only when several 'L' particles exist.
-template<bool FORCE, bool BUSSI, bool WAIT, bool FINALIZE, bool SYS = false>
+//   * WIDE_POLL (folder CTA of k_split_folder): the photon sector is fetched eagerly with the others and a
+//     thread whose record has not arrived re-reads ALL its sectors on every attempt, so the fold is one L2
+//     round trip behind the last record.  When the WHOLE grid polls (k_fused, k_split) that is 4x the
+//     traffic on the same few lines and delays the publishers (force call 23.9 -> 25.4 us, measured), so
+//     there a thread polls one sector at a time.
+template<bool FORCE, bool BUSSI, bool WAIT, bool FINALIZE, bool SYS = false, bool WIDE_POLL = false>
 __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, int G, unsigned long long epoch,
                                               const ForceIn& f, const BussiIn& b, BlockScratch& sc, Scalars* scalars,
                                               bool publish, unsigned long long* dbg = nullptr)
@@ -527,11 +532,24 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
                 {
                 s0 = ld_rec<SYS>(p + 0);
                 s1 = ld_rec<SYS>(p + 1);
-                // the photon's position travels with the other sectors: the one lane that turns out to
-                // hold the candidate then has it without a second, dependent L2 round trip
-                s3 = ld_rec<SYS>(p + 3);
+                // folder: the photon's position travels with the other sectors, so the one lane that turns
+                // out to hold the candidate has it without a second, dependent L2 round trip
+                if (WIDE_POLL)
+                    s3 = ld_rec<SYS>(p + 3);
                 }
-            if (WAIT)
+            if (WAIT && !WIDE_POLL)
+                {
+                if (!sector_ok(s2, epoch))
+                    s2 = read_sector<true, SYS>(p + 2, epoch, late);
+                if (FORCE)
+                    {
+                    if (!sector_ok(s0, epoch))
+                        s0 = read_sector<true, SYS>(p + 0, epoch, late);
+                    if (!sector_ok(s1, epoch))
+                        s1 = read_sector<true, SYS>(p + 1, epoch, late);
+                    }
+                }
+            if (WAIT && WIDE_POLL)
                 {
                 // poll ALL the sectors this thread needs with one round trip per attempt (checking them one
                 // after the other costs a dependent L2 round trip each -- 1-2 us apiece while the grid streams)
@@ -577,7 +595,8 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
                         {
                         mykey = idx;
                         myrec = j;
-                        mys3 = s3;
+                        if (WIDE_POLL)
+                            mys3 = s3;
                         }
                     }
                 }
@@ -596,9 +615,10 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
             const bool i_hold = (wmin != ~0ull) && (mykey == wmin);
             if (i_hold)
                 {
-                s3 = mys3;
-                if (WAIT && !sector_ok(s3, epoch))
-                    s3 = read_sector<true, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 3, epoch, late);
+                if (WIDE_POLL)
+                    s3 = mys3;
+                else
+                    s3 = read_sector<WAIT, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 3, epoch, late);
                 if (!FINALIZE) // a rank-level merge may lose the global vote later: keep the term too
                     s4 = read_sector<WAIT, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 4, epoch, late);
                 }
