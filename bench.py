@@ -489,13 +489,13 @@ def run_b200(args):
             "workload": f"synthetic {n_mol}-particle charged box + 1 photon, CavityForce g=1e-3 omegac=0.01 + "
                         f"BussiReservoir kT=100K tau=5ps (BASELINE configs[1])" + (
                             f"; {world} independent replicas, one per GPU (configs[2])" if world > 1 else ""),
-            "path": "cavb200_step: cavity force + Bussi thermostat in one launch (split-phase kernel), device-resident arrays",
+            "path": "cavb200_step: cavity force + Bussi thermostat in one launch (split-phase kernel with a folder CTA), device-resident arrays",
             "l2": f"inputs larger than L2: rotating over {len(systems)} systems x {116 * N / 1e6:.0f} MB",
             "tuning": {k: h.get_tuning(k) for k in ("variant", "threads", "ctas_per_sm", "unroll", "pdl")},
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_split (cavb200_step)",
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_split_folder (cavb200_step)",
             "algorithmic_bytes_per_particle": STEP_BYTES, "kernel_ms": t_launch, "peak_source": peak_src,
             "isolated": {"kernel_ms": t_step, "achieved": STEP_BYTES * N / (t_step * 1e-3) / 1e9,
                          "frac": STEP_BYTES * N / (t_step * 1e-3) / 1e9 / peak,
