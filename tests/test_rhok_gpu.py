@@ -72,3 +72,34 @@ def test_rhok_deterministic(handle):
     a, _ = gpu_rhok(handle, frames, kvec)
     b, _ = gpu_rhok(handle, frames, kvec)
     assert np.array_equal(a, b)
+
+
+def test_fkt_from_a_gsd_trajectory(tmp_path, handle):
+    """BASELINE configs[4] is phrased on a GSD trajectory (--enable-fkt): frames written and read back with the
+    minimal GSD layer (cav_hoomd_b200/gsdio.py; float32 positions, as HOOMD stores them) feed the batched
+    density-field kernel; compared with the NumPy restatement of compute_density_field on the same frames
+    (reference src/cavitymd/analysis.py:34-47).  Tolerance 1e-9 relative to N (device sincos vs libm)."""
+    from cav_hoomd_b200 import analysis, gsdio, synth
+    from oracle import oracle as O
+    s = synth.make_system(3000, replica=5)
+    rng = np.random.default_rng(0)
+    frames = []
+    for t in range(6):
+        fr = gsdio.system_to_frame(s, step=100 * t)
+        fr.position = (fr.position + rng.normal(scale=0.05 * t, size=fr.position.shape)).astype(np.float32)
+        frames.append(fr)
+    path = str(tmp_path / "traj.gsd")
+    gsdio.write_gsd(path, frames)
+    with gsdio.open_gsd(path) as f:
+        assert len(f) == 6 and [f[i].step for i in range(6)] == [0, 100, 200, 300, 400, 500]
+        pos = np.stack([f[i].position.astype(np.float64) for i in range(len(f))])
+    kvec = analysis.generate_fibonacci_sphere(16) * 0.7
+    field = analysis.DensityField(kvec, handle)
+    rho = field.compute_density_field(pos)
+    for t in range(6):
+        ref = O.numpy_density_field(pos[t], kvec)
+        assert np.abs(rho[t] - ref).max() <= 1e-9 * pos.shape[1]
+    f0 = O.numpy_field_autocorr(rho[0], rho[3])
+    d_rho = capi.DeviceArray.from_numpy(np.stack([rho.real, rho.imag], axis=-1))
+    F = field.autocorrelation(d_rho, 6, 2, 4)
+    assert abs(F[0, 3] - f0) <= 1e-9 * abs(f0)
