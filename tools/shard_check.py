@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--check-n", type=int, default=200_000)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--modes", default="nvlink,nccl")
+    ap.add_argument("--variant", type=int, default=3, help="tuning variant of the handle")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -70,6 +71,7 @@ def main():
 
     for mode in args.modes.split(","):
         h = capi.Handle(local)
+        h.set_tuning(variant=args.variant)
         shard.bootstrap(h, dist, mode)
         # ---- parity on a size the CPU oracle finishes in a second ----
         s = synth.make_system(args.check_n)
