@@ -82,6 +82,7 @@ struct Tuning
     int stamps;          // debug: record per-CTA phase timestamps of the cooperative kernel
     int rhok_threads;
     int rhok_kblock;     // k-vectors handled per thread in the F(k,t) kernel
+    int ke_first;        // folder step kernel: thermostat half first (1) or dipole half first (0)
     };
 
 struct ShardState

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
 //     folder CTA:     fold dipole records -> publish Final(F) | fold KE records -> publish Final(K)
 // The dipole is the correctly rounded sum of the same terms as in the other variants, folded over one
 // record fewer (grid - 1 streaming CTAs): results agree to the last bit or two, not bit for bit.
-template<int UNROLL, int LB>
+template<int UNROLL, int LB, bool KE_FIRST>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_split_folder(ForceIn f, BussiIn b, Partial* recsF, Partial* recsB, Partial* finals, Scalars* scalars,
                    unsigned long long* epoch_ctr, unsigned long long* stamps)
@@ -211,63 +211,112 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
             const unsigned long long ep = real ? epoch : dummy_epoch;
             if (my_stamps && real)
                 my_stamps[1] = globaltimer_ns();
-            combine_phase<true, false, true, true, false, true>(real ? recsF : dummy, (int)g.nblk, ep, f, b, sc, scalars, real,
-                                                   (my_stamps && real) ? my_stamps + 8 * 1024 : nullptr);
-            if (threadIdx.x == 0)
-                publish_final<true>(real ? finals + 0 : dummy + g.nblk, sc.fin, ep);
-            if (my_stamps && real)
-                my_stamps[3] = globaltimer_ns();
-            timeout_f = sc.fin.timeout != 0;
-            __syncthreads();
-            combine_phase<false, true, true, true, false, true>(real ? recsB : dummy, (int)g.nblk, ep, f, b, sc, scalars, real);
-            if (threadIdx.x == 0)
+#pragma unroll
+            for (int half = 0; half < 2; half++)
                 {
-                if (timeout_f)
-                    sc.fin.timeout = 1;
-                publish_final<false>(real ? finals + 1 : dummy + g.nblk + 1, sc.fin, ep);
-                if (real)
-                    *epoch_ctr = epoch; // every streaming CTA has published twice, hence read the counter
+                if ((half == 0) != KE_FIRST)
+                    {
+                    combine_phase<true, false, true, true, false, true>(real ? recsF : dummy, (int)g.nblk, ep, f, b, sc, scalars,
+                                                                        real, (my_stamps && real) ? my_stamps + 8 * 1024 : nullptr);
+                    timeout_f = timeout_f || sc.fin.timeout != 0;
+                    if (threadIdx.x == 0)
+                        {
+                        if (timeout_f)
+                            sc.fin.timeout = 1;
+                        publish_final<true>(real ? finals + 0 : dummy + g.nblk, sc.fin, ep);
+                        }
+                    if (my_stamps && real)
+                        my_stamps[3] = globaltimer_ns();
+                    }
+                else
+                    {
+                    combine_phase<false, true, true, true, false, true>(real ? recsB : dummy, (int)g.nblk, ep, f, b, sc, scalars,
+                                                                        real);
+                    timeout_f = timeout_f || sc.fin.timeout != 0;
+                    if (threadIdx.x == 0)
+                        {
+                        if (timeout_f)
+                            sc.fin.timeout = 1;
+                        publish_final<false>(real ? finals + 1 : dummy + g.nblk + 1, sc.fin, ep);
+                        }
+                    if (my_stamps && real)
+                        my_stamps[5] = globaltimer_ns();
+                    }
+                __syncthreads();
                 }
-            __syncthreads();
+            if (threadIdx.x == 0 && real)
+                *epoch_ctr = epoch; // every streaming CTA has published twice, hence read the counter
             }
-        if (my_stamps)
-            my_stamps[5] = globaltimer_ns();
         pdl_launch_dependents();
         return;
         }
     // ---- streaming CTAs ----
-    reduce_phase<true, false, UNROLL>(f, b, sc, g);
+    // first half: the one whose hand-off has the whole second pass to hide behind; second half: its hand-off
+    // hides behind the first half's write pass.  KE_FIRST = thermostat first (see the launcher).
+    if (!KE_FIRST)
+        reduce_phase<true, false, UNROLL>(f, b, sc, g);
+    else
+        reduce_phase<false, true, UNROLL>(f, b, sc, g);
     const unsigned long long epoch = sc.epoch;
     if (threadIdx.x == 0)
-        publish_record(recsF + g.blk, sc.rec, epoch);
+        publish_record((KE_FIRST ? recsB : recsF) + g.blk, sc.rec, epoch);
     if (my_stamps)
         my_stamps[1] = globaltimer_ns();
     FinalSectors pre;
         {
         Acc a;
-        reduce_loops<false, true, UNROLL>(a, f, b, g);
-        // Final(F) has normally been out since the middle of this pass: fetch it under the merge tree
-        pre = prefetch_final<true>(finals + 0);
-        block_merge<false, true>(a, f, sc);
+        // the first half's Final has normally been out since the middle of this pass: fetch it under the merge tree
+        if (!KE_FIRST)
+            {
+            reduce_loops<false, true, UNROLL>(a, f, b, g);
+            pre = prefetch_final<true>(finals + 0);
+            block_merge<false, true>(a, f, sc);
+            }
+        else
+            {
+            reduce_loops<true, false, UNROLL>(a, f, b, g);
+            pre = prefetch_final<false>(finals + 1);
+            block_merge<true, false>(a, f, sc);
+            }
         }
     if (threadIdx.x == 0)
-        publish_record(recsB + g.blk, sc.rec, epoch);
+        publish_record((KE_FIRST ? recsF : recsB) + g.blk, sc.rec, epoch);
     if (my_stamps)
         my_stamps[2] = globaltimer_ns();
-    const Final finF = take_final<true>(finals + 0, epoch, pre);
-    if (my_stamps)
-        my_stamps[3] = globaltimer_ns();
-    if (!finF.timeout)
+    if (!KE_FIRST)
+        {
+        const Final finF = take_final<true>(finals + 0, epoch, pre);
+        if (my_stamps)
+            my_stamps[3] = globaltimer_ns();
+        if (!finF.timeout)
+            apply_phase<true, false, UNROLL>(finF, f, b, g);
+        if (my_stamps)
+            my_stamps[4] = globaltimer_ns();
+        const Final finK = take_final<false>(finals + 1, epoch, prefetch_final<false>(finals + 1));
+        if (my_stamps)
+            my_stamps[5] = globaltimer_ns();
+        if (finF.timeout || finK.timeout)
+            return;
+        pdl_launch_dependents();
+        apply_phase<false, true, UNROLL>(finK, f, b, g);
+        }
+    else
+        {
+        const Final finK = take_final<false>(finals + 1, epoch, pre);
+        if (my_stamps)
+            my_stamps[3] = globaltimer_ns();
+        if (!finK.timeout)
+            apply_phase<false, true, UNROLL>(finK, f, b, g);
+        if (my_stamps)
+            my_stamps[4] = globaltimer_ns();
+        const Final finF = take_final<true>(finals + 0, epoch, prefetch_final<true>(finals + 0));
+        if (my_stamps)
+            my_stamps[5] = globaltimer_ns();
+        if (finF.timeout || finK.timeout)
+            return;
+        pdl_launch_dependents();
         apply_phase<true, false, UNROLL>(finF, f, b, g);
-    if (my_stamps)
-        my_stamps[4] = globaltimer_ns();
-    const Final finK = take_final<false>(finals + 1, epoch, prefetch_final<false>(finals + 1));
-    if (my_stamps)
-        my_stamps[5] = globaltimer_ns();
-    if (finF.timeout || finK.timeout)
-        return;
-    pdl_launch_dependents();
-    apply_phase<false, true, UNROLL>(finK, f, b, g);
+        }
     if (my_stamps)
         my_stamps[6] = globaltimer_ns();
     }
@@ -297,10 +346,14 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         // the folder pays two extra L2 round trips, which only a full streaming grid hides (65k particles:
         // 11.95 us with the folder, 10.1 us without): small systems take the plain split-phase kernel
         const bool folder = h->tune.variant == 3 && want >= (unsigned long long)max_grid;
-        const void* kern = folder ? (const void*)k_split_folder<UNROLL, LB> : (const void*)k_split<UNROLL, LB>;
+        const void* kern = !folder ? (const void*)k_split<UNROLL, LB>
+                                   : (h->tune.ke_first ? (const void*)k_split_folder<UNROLL, LB, true>
+                                                       : (const void*)k_split_folder<UNROLL, LB, false>);
         int per_sm = 0;
-        if (folder)
-            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split_folder<UNROLL, LB>, threads, 0));
+        if (folder && h->tune.ke_first)
+            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split_folder<UNROLL, LB, true>, threads, 0));
+        else if (folder)
+            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split_folder<UNROLL, LB, false>, threads, 0));
         else
             CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split<UNROLL, LB>, threads, 0));
         if (per_sm < 1)

@@ -19,8 +19,10 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=2)
     ap.add_argument("--unroll", type=int, default=2)
     ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--ke-first", type=int, default=0)
     args = ap.parse_args()
     h = capi.Handle(0)
+    h.set_tuning(ke_first=args.ke_first)
     n_mol = args.n_mol
     base, systems = make(h, n_mol, 8)
     p = capi.Params.make(0.01, 1e-3)
