@@ -81,6 +81,9 @@ __device__ __forceinline__ void acc_zero(Acc& a)
     a.n_L = 0;
     }
 
+// (Measured: the whole-grid fold of k_fused takes 4.25 us the first time through and 2.25 us when it is run a
+// second time in the same launch; rolling this level loop to shrink the code -- 5664 -> 3208 instructions --
+// made it slower, 23.7 -> 24.95 us per force call, so instruction fetch is not what the first pass pays for.)
 template<bool FORCE, bool BUSSI> __device__ __forceinline__ void warp_tree(Acc& a)
     {
 #pragma unroll
@@ -428,8 +431,18 @@ __device__ __forceinline__ void publish_record(Partial* dst, const Partial& src,
 // Strong (L2) read of one sector; WAIT: poll until it carries this launch's epoch (bounded).
 // SYS: the records are written by PEER GPUs over NVLink into this GPU's memory (sharded mode):
 // system-scope loads, and a timeout that tolerates ranks starting late.
+// Sleep between two polls of a sector that has not arrived (A/B on one box, 1M particles, profiles/poll_r1a.txt):
+// whole-grid folds (k_fused, k_split) want it short -- 64 -> 16 ns: Bussi call 17.7 -> 16.7 us, force call
+// 23.6 -> 23.35 us (0 ns is no better); the streaming CTAs of k_split_folder waiting for a Final record want it
+// long -- every warp of the grid polls the same sector: 0 / 64 / 300 ns give 31.88 / 31.87 / 31.63 us per step.
+#ifndef CAVB_POLL_NS
+#define CAVB_POLL_NS 16
+#endif
+#ifndef CAVB_FINAL_POLL_NS
+#define CAVB_FINAL_POLL_NS 300
+#endif
 template<bool SYS> __device__ __forceinline__ double4 ld_rec(const double4* p) { return SYS ? ld256_sys(p) : ld256_cg(p); }
-template<bool WAIT, bool SYS = false>
+template<bool WAIT, bool SYS = false, int POLL_NS = CAVB_POLL_NS>
 __device__ __forceinline__ double4 read_sector(const double4* p, unsigned long long epoch, bool& late)
     {
     double4 s = ld_rec<SYS>(p);
@@ -440,7 +453,8 @@ __device__ __forceinline__ double4 read_sector(const double4* p, unsigned long l
             const unsigned long long t0 = globaltimer_ns();
             do
                 {
-                __nanosleep(64);
+                if (POLL_NS > 0)
+                    __nanosleep(POLL_NS);
                 s = ld_rec<SYS>(p);
                 if (globaltimer_ns() - t0 > (SYS ? PEER_TIMEOUT_NS : HANDOFF_TIMEOUT_NS)) // never hang the GPU
                     {
@@ -537,16 +551,36 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
                 if (WIDE_POLL)
                     s3 = ld_rec<SYS>(p + 3);
                 }
-            if (WAIT && !WIDE_POLL)
+            if (!WIDE_POLL)
                 {
-                if (!sector_ok(s2, epoch))
+                // whole-grid fold: poll ONE sector (every CTA polls every record); once it is there, fetch the
+                // other sectors that were stale at first look TOGETHER -- and, for the rare record that holds an
+                // 'L' candidate, its position sector with them -- instead of one dependent round trip each
+                bool refetch = false;
+                if (WAIT && !sector_ok(s2, epoch))
+                    {
                     s2 = read_sector<true, SYS>(p + 2, epoch, late);
+                    refetch = true;
+                    }
                 if (FORCE)
                     {
-                    if (!sector_ok(s0, epoch))
-                        s0 = read_sector<true, SYS>(p + 0, epoch, late);
-                    if (!sector_ok(s1, epoch))
-                        s1 = read_sector<true, SYS>(p + 1, epoch, late);
+                    const bool cand = dbits(s2.y) != ~0ull;
+                    if (WAIT && (refetch || !sector_ok(s0, epoch) || !sector_ok(s1, epoch)))
+                        {
+                        s0 = ld_rec<SYS>(p + 0);
+                        s1 = ld_rec<SYS>(p + 1);
+                        }
+                    if (cand)
+                        s3 = ld_rec<SYS>(p + 3);
+                    if (WAIT)
+                        {
+                        if (!sector_ok(s0, epoch))
+                            s0 = read_sector<true, SYS>(p + 0, epoch, late);
+                        if (!sector_ok(s1, epoch))
+                            s1 = read_sector<true, SYS>(p + 1, epoch, late);
+                        if (cand && !sector_ok(s3, epoch))
+                            s3 = read_sector<true, SYS>(p + 3, epoch, late);
+                        }
                     }
                 }
             if (WAIT && WIDE_POLL)
@@ -595,8 +629,7 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
                         {
                         mykey = idx;
                         myrec = j;
-                        if (WIDE_POLL)
-                            mys3 = s3;
+                        mys3 = s3;
                         }
                     }
                 }
@@ -615,10 +648,7 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
             const bool i_hold = (wmin != ~0ull) && (mykey == wmin);
             if (i_hold)
                 {
-                if (WIDE_POLL)
-                    s3 = mys3;
-                else
-                    s3 = read_sector<WAIT, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 3, epoch, late);
+                s3 = mys3; // fetched with the record's other sectors
                 if (!FINALIZE) // a rank-level merge may lose the global vote later: keep the term too
                     s4 = read_sector<WAIT, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 4, epoch, late);
                 }
@@ -1036,13 +1066,13 @@ __device__ __forceinline__ Final take_final(const Partial* src, unsigned long lo
     fin.photon_local = -1;
     double4 s0 = pre.s0, s1 = pre.s1, s2 = pre.s2;
     if (!sector_ok(s2, epoch))
-        s2 = read_sector<true>(p + 2, epoch, late);
+        s2 = read_sector<true, false, CAVB_FINAL_POLL_NS>(p + 2, epoch, late);
     if (FORCE)
         {
         if (!sector_ok(s0, epoch))
-            s0 = read_sector<true>(p + 0, epoch, late);
+            s0 = read_sector<true, false, CAVB_FINAL_POLL_NS>(p + 0, epoch, late);
         if (!sector_ok(s1, epoch))
-            s1 = read_sector<true>(p + 1, epoch, late);
+            s1 = read_sector<true, false, CAVB_FINAL_POLL_NS>(p + 1, epoch, late);
         fin.Dq[0] = s0.x;
         fin.Dq[1] = s0.y;
         fin.FL[0] = s0.z;
