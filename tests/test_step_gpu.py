@@ -148,3 +148,23 @@ def test_step_back_to_back_epochs(handle, coracle, variant):
         if it >= 36:
             f = d["force"].numpy(st.ptr)
             assert np.abs(f - refs[k]["force"]).max() <= 1e-10 * np.abs(refs[k]["force"]).max()
+
+
+@pytest.mark.parametrize("n_mol", [1_000_000, 16_000_000])
+def test_step_full_sizes(handle, coracle, n_mol):
+    """BASELINE.json sizes (configs[1]: 1M, configs[3]: 16M), default tuning (folder step kernel on a full grid):
+    oracle parity, plus the size-independent properties of the thermostat half -- the kinetic energy after the
+    rescale is alpha^2 times the one before (to rounding), velocities keep their direction, masses untouched."""
+    handle.set_tuning(variant=3, threads=384, ctas_per_sm=2, unroll=2)
+    s = synth.make_system(n_mol)
+    a = args_for(n_mol)
+    out = run_step(handle, s, 0, n_mol, a)
+    check_against_oracle(coracle, s, 0, n_mol, a, out)
+    f, v, en, dip, ph, bo = out
+    assert ph == n_mol and bo["err"] == 0.0
+    ke0 = 0.5 * np.sum(s.vel[:n_mol, 3] * np.sum(s.vel[:n_mol, :3] ** 2, axis=1))
+    ke1 = 0.5 * np.sum(v[:n_mol, 3] * np.sum(v[:n_mol, :3] ** 2, axis=1))
+    assert abs(bo["ke"] - ke0) <= 1e-12 * ke0
+    assert abs(ke1 - bo["alpha"] ** 2 * ke0) <= 1e-12 * ke0
+    assert np.array_equal(v[:, 3], s.vel[:, 3])
+    assert np.array_equal(v[n_mol], s.vel[n_mol])  # the photon is outside the thermostatted group
