@@ -83,18 +83,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     if (my_stamps)
         my_stamps[1] = globaltimer_ns();
     const unsigned long long epoch = sc.epoch;
-#ifdef CAVB_EXP_DOUBLE_COMBINE
-#pragma unroll 1
-    for (int pass = 0; pass < 2; pass++)
-        {
-        if (my_stamps && pass == 1)
-            my_stamps[2] = globaltimer_ns();
-        combine_phase<FORCE, BUSSI, true, true>(recs, (int)gridDim.x, epoch, f, b, sc, scalars, blockIdx.x == 0 && pass == 1,
-                                                my_stamps);
-        }
-#else
     combine_phase<FORCE, BUSSI, true, true>(recs, (int)gridDim.x, epoch, f, b, sc, scalars, blockIdx.x == 0, my_stamps);
-#endif
     if (my_stamps)
         my_stamps[3] = globaltimer_ns();
     if (blockIdx.x == 0 && threadIdx.x == 0)
