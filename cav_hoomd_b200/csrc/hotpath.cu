@@ -5,6 +5,9 @@
 #ifndef CAVB_FOLDER_WARMUP
 #define CAVB_FOLDER_WARMUP 1
 #endif
+#ifndef CAVB_VEL_PREFETCH
+#define CAVB_VEL_PREFETCH 4 // velocities per thread fetched before the wait for alpha (k_split_folder)
+#endif
 
 namespace cavb
     {
@@ -292,13 +295,24 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
             apply_phase<true, false, UNROLL>(finF, f, b, g);
         if (my_stamps)
             my_stamps[4] = globaltimer_ns();
-        const Final finK = take_final<false>(finals + 1, epoch, prefetch_final<false>(finals + 1));
+        const FinalSectors preK = prefetch_final<false>(finals + 1);
+        const bool contiguous = b.gidx == nullptr && b.first == 0;
+        VelPrefetch<CAVB_VEL_PREFETCH> pv;
+        if (contiguous)
+            pv = prefetch_vel<CAVB_VEL_PREFETCH>(b, g);
+        const Final finK = take_final<false>(finals + 1, epoch, preK);
         if (my_stamps)
             my_stamps[5] = globaltimer_ns();
         if (finF.timeout || finK.timeout)
             return;
         pdl_launch_dependents();
-        apply_phase<false, true, UNROLL>(finK, f, b, g);
+        if (contiguous)
+            {
+            if (b.rescale && finK.bussi_ok && finK.alpha != 1.0) // as apply_phase
+                rescale_prefetched<CAVB_VEL_PREFETCH, UNROLL>(finK.alpha, b, g, pv);
+            }
+        else
+            apply_phase<false, true, UNROLL>(finK, f, b, g);
         }
     else
         {
