@@ -153,6 +153,102 @@ __global__ void __launch_bounds__(256)
         *ticket = 0ull;
     }
 
+// Step one of the thermostatted harness with the NEXT cavity force's reduce pass folded in (SURVEY.md 8f.1 + 8f.2):
+// the kick uses the rank-1 force of the previous Final record, the drift produces the new position, and the
+// dipole term charge * (r_new + image L) of that new position is accumulated on the spot
+// (src/CavityForceCompute.cc:107-109,124) -- positions are never read a second time.  The last CTA to take a
+// ticket folds the CTA records and leaves the new Scalars / Final for step two.  One launch replaces
+// cavb200_nvt_step_one_rank1 + cavb200_force_rank1.
+__global__ void __launch_bounds__(256, 3)
+    k_md_one(double4* pos, double4* vel, const double4* force_other, uint32_t N, double dt, BussiIn b, Scalars* scalars,
+             Rank1In r1, ForceIn fnew, Partial* recs, unsigned long long* ticket, Final* fin_out)
+    {
+    __shared__ BlockScratch sc;
+    __shared__ double s_alpha;
+    __shared__ Final s_fin;
+    __shared__ int s_last;
+    if (threadIdx.x == 0)
+        {
+        sc.flags = 0u;
+        s_fin = *r1.fin;
+        double alpha = 1.0;
+        if (b.rescale && b.n > 0)
+            {
+            int ok = 1;
+            const double KE = scalars->ke;
+            alpha = bussi_alpha(KE, b, ok);
+            if (blockIdx.x == 0)
+                {
+                if (ok)
+                    {
+                    const double inst = __dmul_rn(KE, __dadd_rn(1.0, -__dmul_rn(alpha, alpha))); // BussiReservoirThermostat.h:86-95
+                    scalars->alpha = alpha;
+                    scalars->inst = inst;
+                    scalars->cumulative = __dadd_rn(scalars->cumulative, inst);
+                    }
+                else
+                    scalars->err = 1.0;
+                }
+            }
+        s_alpha = alpha;
+        }
+    __syncthreads();
+    const double alpha = s_alpha;
+    const unsigned long long lo = b.first, hi = (unsigned long long)b.first + b.n;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    Acc a;
+    acc_zero(a);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+        {
+        double4 v = ld256(vel + i);
+        double4 p = ld256(pos + i);
+        const double c = __ldg(fnew.charge + i);
+        const int ix = __ldg(fnew.image + 3 * i + 0), iy = __ldg(fnew.image + 3 * i + 1), iz = __ldg(fnew.image + 3 * i + 2);
+        double4 f = force_of(i, c, s_fin, r1.f);
+        if (force_other)
+            {
+            const double4 fo = ld256(force_other + i);
+            f.x = __dadd_rn(fo.x, f.x);
+            f.y = __dadd_rn(fo.y, f.y);
+            f.z = __dadd_rn(fo.z, f.z);
+            }
+        if (i >= lo && i < hi)
+            {
+            v.x = __dmul_rn(v.x, alpha);
+            v.y = __dmul_rn(v.y, alpha);
+            v.z = __dmul_rn(v.z, alpha);
+            }
+        const double hm = __ddiv_rn(__dmul_rn(0.5, dt), v.w);
+        v.x = __dadd_rn(v.x, __dmul_rn(hm, f.x));
+        v.y = __dadd_rn(v.y, __dmul_rn(hm, f.y));
+        v.z = __dadd_rn(v.z, __dmul_rn(hm, f.z));
+        p.x = __dadd_rn(p.x, __dmul_rn(dt, v.x));
+        p.y = __dadd_rn(p.y, __dmul_rn(dt, v.y));
+        p.z = __dadd_rn(p.z, __dmul_rn(dt, v.z));
+        st256(vel + i, v);
+        st256(pos + i, p);
+        take_particle(a, (unsigned int)i, p, c, ix, iy, iz, fnew);
+        }
+    block_merge<true, false>(a, fnew, sc);
+    if (threadIdx.x == 0)
+        {
+        publish_record(recs + blockIdx.x, sc.rec, 0ull);
+        __threadfence();
+        const unsigned long long t = atom_acq_rel_add_u64(ticket, 1ull);
+        s_last = (t == (unsigned long long)gridDim.x - 1);
+        }
+    __syncthreads();
+    if (!s_last)
+        return;
+    BussiIn bz = {};
+    combine_phase<true, false, false, true>(recs, (int)gridDim.x, 0ull, fnew, bz, sc, scalars, true);
+    if (threadIdx.x == 0)
+        {
+        *fin_out = sc.fin;
+        *ticket = 0ull;
+        }
+    }
+
 template<bool DRIFT>
 __global__ void __launch_bounds__(256) k_nve(double4* pos, double4* vel, const double4* force, uint32_t N, double dt)
     {
@@ -348,6 +444,54 @@ extern "C" int cavb200_nvt_step_two_rank1(cavb200_handle* h, double* vel, const 
     if (rc)
         return rc;
     return nvt_two(h, vel, force_other, N, dt, group_first, n_group, &r, stream);
+    }
+
+extern "C" int cavb200_md_step_one(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                                   const double* charge, const int32_t* image, uint32_t N, double dt, double Lx, double Ly,
+                                   double Lz, uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
+                                   uint32_t n_group, const cavb200_bussi_args* bussi, void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    if (!pos || !vel || !charge || !image || !params || (unsigned long long)group_first + n_group > N)
+        return (int)cudaErrorInvalidValue;
+    if (mis32(pos) || mis32(vel) || mis32(force_other) || (reinterpret_cast<uintptr_t>(image) & 3))
+        return (int)cudaErrorMisalignedAddress;
+    Rank1In r;
+    const int rc = fill_rank1(h, r, charge, pos, L_typeid, params->couplstr);
+    if (rc)
+        return rc;
+    ForceIn fnew = {};
+    fnew.pos = reinterpret_cast<const double4*>(pos);
+    fnew.charge = charge;
+    fnew.image = image;
+    fnew.N = N;
+    fnew.Lx = Lx;
+    fnew.Ly = Ly;
+    fnew.Lz = Lz;
+    fnew.L_typeid = L_typeid;
+    fnew.g = params->couplstr;
+    fnew.K = params->K;
+    fill_force_constants(fnew);
+    BussiIn b = {};
+    b.first = group_first;
+    b.n = n_group;
+    b.rescale = bussi != nullptr && bussi->deltaT != 0.0;
+    if (bussi)
+        fill_bussi_constants(b, bussi);
+    unsigned long long want = ((unsigned long long)N + 255) / 256;
+    unsigned long long cap = (unsigned long long)h->num_sms * 3; // one wave of 3 CTAs per SM (85-register budget)
+    if (cap > (unsigned long long)MAX_PARTIALS)
+        cap = MAX_PARTIALS;
+    const int grid = (int)(want < cap ? want : cap);
+    k_md_one<<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)pos, (double4*)vel, (const double4*)force_other, N, dt, b,
+                                                      h->scalars, r, fnew, h->partials, h->counters + 4,
+                                                      const_cast<Final*>(rank1_final(h)));
+    CAVB_CHECK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
     }
 
 extern "C" int cavb200_net_force_add_rank1(cavb200_handle* h, double* net_force, const double* charge, const double* pos,

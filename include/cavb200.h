@@ -186,6 +186,17 @@ int cavb200_net_force_add_rank1(cavb200_handle* h, double* net_force, const doub
 int cavb200_nvt_step_one_rank1(cavb200_handle* h, double* pos, double* vel, const double* force_other,
                                const double* charge, uint32_t N, double dt, uint32_t L_typeid, double couplstr,
                                uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, void* stream);
+/*   cavb200_md_step_one      step one of the harness with the NEXT cavity force's reduce pass inside it: the kick uses
+ *                            the rank-1 force of the previous result, the drift produces r_new, and the dipole term
+ *                            charge * (r_new + image L) (reference src/CavityForceCompute.cc:107-109,124) is accumulated
+ *                            on the spot, so the positions are not read a second time.  Replaces
+ *                            cavb200_nvt_step_one_rank1 + cavb200_force_rank1 by ONE launch; a step is
+ *                            cavb200_md_step_one ; cavb200_nvt_step_two_rank1  (220 algorithmic B/particle).
+ *                            Energies / dipole / photon index afterwards as cavb200_force_read. */
+int cavb200_md_step_one(cavb200_handle* h, double* pos, double* vel, const double* force_other, const double* charge,
+                        const int32_t* image, uint32_t N, double dt, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                        const cavb200_params* params, uint32_t group_first, uint32_t n_group,
+                        const cavb200_bussi_args* bussi, void* stream);
 int cavb200_nvt_step_two_rank1(cavb200_handle* h, double* vel, const double* force_other, const double* charge,
                                const double* pos, uint32_t N, double dt, uint32_t L_typeid, double couplstr,
                                uint32_t group_first, uint32_t n_group, void* stream);

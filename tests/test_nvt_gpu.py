@@ -228,3 +228,69 @@ def test_nvt_rank1_with_other_forces(handle, coracle):
     assert _rel(d["vel"].numpy()[:, :3], v2) <= 1e-12
     ke = 0.5 * np.sum(s.vel[:n_mol, 3] * np.sum(v2[:n_mol] ** 2, axis=1))
     assert abs(handle.bussi_read()["ke"] - ke) <= 1e-12 * ke
+
+
+# ---- step one with the next force's reduce inside (cavb200_md_step_one) ----------------------------
+@pytest.mark.parametrize("photon", ["last", "middle", "duplicated"])
+@pytest.mark.parametrize("n_mol", [1, 300, 20000, 200000])
+def test_md_step_one_matches_oracle_and_rank1_path(handle, coracle, n_mol, photon):
+    """cavb200_md_step_one ; cavb200_nvt_step_two_rank1 against orc_nvt_step (same tolerances as above) and
+    against the three-launch rank-1 path: identical trajectories to <= 1e-14 (the dipole of the new positions
+    is the same compensated sum over another partition of the particles)."""
+    steps, dt = 8, synth.DT_1FS
+    s = synth.make_system(n_mol, replica=13, photon=photon)
+    first, n = (0, n_mol) if photon == "last" else (0, s.N)
+    dof = max(3.0 * n - 3.0, 1.0)
+    p = capi.Params.make(OMEGAC, G, PHMASS)
+    st = capi.Stream()
+
+    def run(fused):
+        d = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+        handle.bussi_reset(st.ptr)
+        handle.force_rank1(d["pos"], d["charge"], d["image"], s.N, s.box, s.L_typeid, p, st.ptr)
+        handle.bussi_ke(d["vel"], None, first, n, st.ptr)
+        hist = []
+        for t in range(steps):
+            r, gm = rng.bussi_draws(t, 5, 0, dof)
+            a = capi.BussiArgs(synth.KT_100K, synth.TAU_5PS, dt, dof, r, gm)
+            if fused:
+                handle.md_step_one(d["pos"], d["vel"], None, d["charge"], d["image"], s.N, dt, s.box, s.L_typeid, p, first, n,
+                                   a, st.ptr)
+            else:
+                handle.nvt_step_one_rank1(d["pos"], d["vel"], None, d["charge"], s.N, dt, s.L_typeid, G, first, n, a, st.ptr)
+                handle.force_rank1(d["pos"], d["charge"], d["image"], s.N, s.box, s.L_typeid, p, st.ptr)
+            handle.nvt_step_two_rank1(d["vel"], None, d["charge"], d["pos"], s.N, dt, s.L_typeid, G, first, n, st.ptr)
+            b = handle.bussi_read(st.ptr)
+            en, dip, ph = handle.force_read(st.ptr)
+            hist.append((b["alpha"], b["ke"], b["cumulative"], en, dip, ph))
+        return d["pos"].numpy(st.ptr), d["vel"].numpy(st.ptr), hist
+
+    pa, va, ha = run(False)
+    pb, vb, hb = run(True)
+    assert _rel(pb[:, :3], pa[:, :3]) <= 1e-14 and _rel(vb[:, :3], va[:, :3]) <= 1e-14
+    for x, y in zip(ha, hb):
+        assert abs(x[0] - y[0]) <= 1e-14 * abs(x[0]) and abs(x[1] - y[1]) <= 1e-13 * abs(x[1]) and x[5] == y[5]
+        assert np.allclose(x[3], y[3], rtol=1e-13, atol=0) and np.allclose(x[4], y[4], rtol=1e-12, atol=1e-9)
+    # oracle arm
+    pos, vel, force = s.pos.copy(), s.vel.copy(), np.zeros((s.N, 4))
+    force[:] = coracle.cavity_force(pos, s.charge, s.image, s.box, s.L_typeid, OMEGAC, G, PHMASS)["force"]
+    idx = np.arange(first, first + n, dtype=np.uint32)
+    ke = np.array([coracle.kinetic_energy(vel, idx)])
+    res = np.zeros(2)
+    for t in range(steps):
+        r, gm = rng.bussi_draws(t, 5, 0, dof)
+        a_ref, en_ref = coracle.nvt_step(pos, vel, s.charge, s.image, force, s.box, s.L_typeid, OMEGAC, G, PHMASS, dt, first, n,
+                                         dof, synth.KT_100K, synth.TAU_5PS, r, gm, res, ke)
+        assert abs(hb[t][0] - a_ref) <= 1e-12 * abs(a_ref)
+        assert abs(hb[t][1] - ke[0]) <= 1e-10 * abs(ke[0])
+        assert np.allclose(hb[t][3], en_ref, rtol=1e-10, atol=1e-300)
+    assert _rel(pb[:, :3], pos[:, :3]) <= 1e-10 and _rel(vb[:, :3], vel[:, :3]) <= 1e-10
+    assert np.array_equal(pb[:, 3].view(np.uint64), s.pos[:, 3].view(np.uint64)) and np.array_equal(vb[:, 3], s.vel[:, 3])
+
+
+def test_md_step_one_argument_errors(handle):
+    a = capi.DeviceArray((8, 4), np.float64)
+    p = capi.Params.make(OMEGAC, G, PHMASS)
+    with pytest.raises(capi.CavbError):
+        handle.md_step_one(a, a, None, None, a, 8, 1.0, (1.0, 1.0, 1.0), 2, p, 0, 8)
+    handle.md_step_one(None, None, None, None, None, 0, 1.0, (1.0, 1.0, 1.0), 2, p, 0, 0)  # N == 0: no-op
