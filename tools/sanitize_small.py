@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """tools/sanitize_small.py -- one small invocation of every kernel of libcavb200 (for compute-sanitizer):
-force, Bussi, step (variants 0/1/2/3), index-list group, sharded step (one rank), NVE kicks, rhok, fkt,
-host-buffer step.  Sizes are small so the bounded hand-off spins survive the sanitizer's slowdown."""
+force, Bussi, step (variants 0/1/2/3), index-list group, sharded step (one rank), NVE / NVT / rank-1 harness steps,
+md_step_one, net-force add, trackers, rhok, fkt, host-buffer step (blocking and slots).  Sizes are small so the bounded hand-off spins survive the sanitizer's slowdown."""
 import os
 import sys
 
@@ -31,7 +31,29 @@ def main():
         h.shard_step(dev["pos"], dev["charge"], dev["image"], d_f, dev["vel"], s.N, 0, s.box, s.L_typeid, p, 0, n_mol, a)
         h.nve_kick_drift(dev["pos"], dev["vel"], d_f, s.N, 1.0)
         h.nve_half_kick(dev["vel"], d_f, s.N, 1.0)
+        # harness steps (8f.1, 8f.2), trackers (8f.4)
+        d_net = capi.DeviceArray.from_numpy(np.zeros((s.N, 4)))
+        h.bussi_ke(dev["vel"], None, 0, n_mol)
+        h.nvt_step_one(dev["pos"], dev["vel"], d_f, s.N, 1.0, 0, n_mol, a)
+        h.nvt_step_two(dev["vel"], d_f, s.N, 1.0, 0, n_mol)
+        h.force_rank1(dev["pos"], dev["charge"], dev["image"], s.N, s.box, s.L_typeid, p)
+        h.net_force_add_rank1(d_net, dev["charge"], dev["pos"], s.N, s.L_typeid, 1e-3)
+        h.nvt_step_one_rank1(dev["pos"], dev["vel"], d_net, dev["charge"], s.N, 1.0, s.L_typeid, 1e-3, 0, n_mol, a)
+        h.md_step_one(dev["pos"], dev["vel"], None, dev["charge"], dev["image"], s.N, 1.0, s.box, s.L_typeid, p, 0, n_mol, a)
+        h.nvt_step_two_rank1(dev["vel"], d_net, dev["charge"], dev["pos"], s.N, 1.0, s.L_typeid, 1e-3, 0, n_mol)
+        h.track_open(3)
+        h.track_set_reference()
+        for t in range(5):
+            h.track_record(t, dev["vel"], s.N)
+        rec, total = h.track_read(8)
+        assert total == 5 and len(rec) == 3
         capi.sync()
+        bufs = [dict(pos=s.pos.copy(), charge=s.charge.copy(), image=s.image.copy(), force=np.zeros((s.N, 4)), vel=s.vel.copy())
+                for _ in range(3)]
+        for k, q in enumerate(bufs):
+            h.step_host_submit(k, q["pos"], q["charge"], q["image"], q["force"], q["vel"], s.N, s.box, s.L_typeid, p, 0, n_mol, a)
+        for k in range(3):
+            h.step_host_wait(k)
         en, bo = h.step_host(s.pos, s.charge, s.image, np.zeros((s.N, 4)), s.vel.copy(), s.N, s.box, s.L_typeid, p, 0, n_mol, a)
         frames = np.ascontiguousarray(np.stack([s.pos[:, :3], s.pos[:, :3] + 0.1]))
         kvec = synth.fibonacci_sphere(7)
