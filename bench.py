@@ -386,12 +386,13 @@ def run_b200(args):
     #   folded  nvt_step_one ; force ; nvt_step_two          thermostat inside the kicks, 340 B/particle
     #   rank1   nvt_step_one_rank1 ; force_rank1 ; nvt_step_two_rank1   cavity force never stored, 260 B/particle
     #   rank1_reduce_in_step_one   md_step_one ; nvt_step_two_rank1       next dipole reduce inside step one, 220 B/particle
+    #   one_launch                 md_step_fused                          step two of t-1 + step one of t, 148 B/particle
     md = {}
     md_steps = max(20, args.steps // 10)
     for d in systems:
         h.bussi_ke(d.vel, None, 0, n_mol, st)
     h.force_rank1(systems[0].pos, systems[0].charge, systems[0].image, N, base.box, base.L_typeid, params, st)
-    for kind, nbytes in (("folded", 340), ("rank1", 260), ("rank1_reduce_in_step_one", 220)):
+    for kind, nbytes in (("folded", 340), ("rank1", 260), ("rank1_reduce_in_step_one", 220), ("one_launch", 148)):
         def md_step(k):
             d = systems[k % len(systems)]
             a = bargs[k % len(bargs)]
@@ -403,9 +404,11 @@ def run_b200(args):
                 h.nvt_step_one_rank1(d.pos, d.vel, None, d.charge, N, synth.DT_1FS, d.L_typeid, COUPLSTR, 0, n_mol, a, st)
                 h.force_rank1(d.pos, d.charge, d.image, N, d.box, d.L_typeid, params, st)
                 h.nvt_step_two_rank1(d.vel, None, d.charge, d.pos, N, synth.DT_1FS, d.L_typeid, COUPLSTR, 0, n_mol, st)
-            else:
+            elif kind == "rank1_reduce_in_step_one":
                 h.md_step_one(d.pos, d.vel, None, d.charge, d.image, N, synth.DT_1FS, d.box, d.L_typeid, params, 0, n_mol, a, st)
                 h.nvt_step_two_rank1(d.vel, None, d.charge, d.pos, N, synth.DT_1FS, d.L_typeid, COUPLSTR, 0, n_mol, st)
+            else:
+                h.md_step_fused(d.pos, d.vel, None, d.charge, d.image, N, synth.DT_1FS, d.box, d.L_typeid, params, 0, n_mol, a, st)
         for k in range(5):
             md_step(k)
         e0, e1 = capi.Event(), capi.Event()
@@ -546,7 +549,7 @@ def run_b200(args):
                              "frac": BUSSI_BYTES * n_mol / (t_bussi * 1e-3) / 1e9 / peak},
         },
         "harness_md_step": {"note": "kick+drift, cavity force, kick with the Bussi thermostat folded in (repo's own "
-                                    "velocity-Verlet harness, not HOOMD's integrator); 3 launches per step, 2 for rank1_reduce_in_step_one", **md},
+                                    "velocity-Verlet harness, not HOOMD's integrator); 3 launches per step, 2 for rank1_reduce_in_step_one, 1 for one_launch", **md},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 52 * N + 32 * n_mol,
                 "d2h_bytes_per_step": 32 * N + 32 * n_mol + 160, "steps": e2e_steps,
                 "path": f"cavb200_step_host_submit/_wait over {E2E_SLOTS} host-resident systems (next upload under "

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "cavb200_nvt_step_one_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _dbl, _u32, _dbl, _u32, _u32, _BP, _vp]),
     "cavb200_md_step_one": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _dbl, _u32, _PP, _u32, _u32, _BP,
                                       _vp]),
+    "cavb200_md_step_fused": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _dbl, _u32, _PP, _u32, _u32, _BP,
+                                        _vp]),
     "cavb200_nvt_step_two_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _dbl, _u32, _dbl, _u32, _u32, _vp]),
     "cavb200_track_open": (C.c_int, [_vp, _u32]),
     "cavb200_track_set_reference": (C.c_int, [_vp, _vp]),
@@ -423,6 +425,13 @@ class Handle:
                                            dt, box[0], box[1], box[2], L_typeid & 0xFFFFFFFF, C.byref(params), group_first,
                                            n_group, C.byref(bussi) if bussi is not None else None, stream),
               "cavb200_md_step_one")
+
+    def md_step_fused(self, pos, vel, force_other, charge, image, N, dt, box, L_typeid, params, group_first, n_group,
+                      bussi=None, stream=None):
+        check(self.lib.cavb200_md_step_fused(self.h, _ptr(pos), _ptr(vel), _ptr(force_other), _ptr(charge), _ptr(image), N,
+                                             dt, box[0], box[1], box[2], L_typeid & 0xFFFFFFFF, C.byref(params),
+                                             group_first, n_group, C.byref(bussi) if bussi is not None else None, stream),
+              "cavb200_md_step_fused")
 
     def nvt_step_two_rank1(self, vel, force_other, charge, pos, N, dt, L_typeid, couplstr, group_first, n_group,
                            stream=None):

@@ -181,6 +181,7 @@ static int* tuning_slot(cavb::Tuning* t, const char* key)
     if (!strcmp(key, "rhok_threads")) return &t->rhok_threads;
     if (!strcmp(key, "rhok_kblock")) return &t->rhok_kblock;
     if (!strcmp(key, "ke_first")) return &t->ke_first;
+    if (!strcmp(key, "md_shape")) return &t->md_shape;
     return nullptr;
     }
 

@@ -82,6 +82,7 @@ struct Tuning
     int stamps;          // debug: record per-CTA phase timestamps of the cooperative kernel
     int rhok_threads;
     int rhok_kblock;     // k-vectors handled per thread in the F(k,t) kernel
+    int md_shape;        // cavb200_md_step_fused launch shape: 0 = one 768-thread CTA per SM (default), 1 = two 384-thread CTAs
     int ke_first;        // folder step kernel: thermostat half first (1) or dipole half first (0)
     };
 

@@ -249,6 +249,192 @@ __global__ void __launch_bounds__(256, 3)
         }
     }
 
+// ONE launch per MD step (SURVEY.md 8f.1 + 8f.2 taken to the end): the second half kick of the previous step, the
+// Bussi thermostat, the first half kick and the drift of this step and the dipole reduce of the new positions,
+//     v1 = v + dt/2 f/m            (f = f_other + rank-1 cavity force of the previous Final record)
+//     KE = 1/2 sum_group m |v1|^2  -> alpha (compute_rescale_factor, reservoir bookkeeping)
+//     v2 = alpha v1 + dt/2 f/m ;  r += dt v2 ;  d += charge (r + image L)
+// i.e. cavb200_nvt_step_two_rank1 of step t-1 followed by cavb200_md_step_one of step t, with every array moved
+// once: vel 32 + 32, pos 32 + 32, charge 8, image 12 = 148 B/particle (the velocities are read again for the second
+// pass, an L2 hit at 1M particles).  Structure of k_split_folder: 295 streaming CTAs, one folder CTA.
+//     streaming CTA:  pass 1 (v1 on the fly, KE) -> publish | take alpha | pass 2 (v2, r, dipole) -> publish
+//     folder CTA:     fold KE records -> alpha -> Final(K) | fold dipole records -> Scalars, Final for the next step
+template<int LB, int U2>
+__global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
+    k_md_fused(double4* pos, double4* vel, const double4* force_other, uint32_t N, double dt, BussiIn b, Rank1In r1,
+               ForceIn fnew, Partial* recsF, Partial* recsB, Partial* finals, Scalars* scalars,
+               unsigned long long* epoch_ctr, Final* fin_out)
+    {
+    __shared__ BlockScratch sc;
+    __shared__ Final s_fin;
+    pdl_wait();
+    if (threadIdx.x == 0)
+        {
+        sc.flags = 0u;
+        sc.epoch = ld_relaxed_u64(epoch_ctr) + 1ull;
+        s_fin = *r1.fin;
+        }
+    __syncthreads();
+    const unsigned long long epoch = sc.epoch;
+    StreamGrid g;
+    g.nblk = gridDim.x - 1;
+    g.blk = blockIdx.x - 1;
+    if (blockIdx.x == 0)
+        {
+        // ---- folder ----
+        ForceIn fz = fnew;
+        combine_phase<false, true, true, true, false, true>(recsB, (int)g.nblk, epoch, fz, b, sc, scalars, true);
+        const bool timeout_k = sc.fin.timeout != 0;
+        if (threadIdx.x == 0)
+            publish_final<false>(finals + 1, sc.fin, epoch);
+        __syncthreads();
+        combine_phase<true, false, true, true, false, true>(recsF, (int)g.nblk, epoch, fnew, b, sc, scalars, true);
+        if (threadIdx.x == 0)
+            {
+            if (timeout_k)
+                sc.fin.timeout = 1;
+            *fin_out = sc.fin; // Dq, F_L, photon index of the NEW positions: the next launch's kicks use it
+            *epoch_ctr = epoch;
+            }
+        pdl_launch_dependents();
+        return;
+        }
+    // ---- streaming CTAs ----
+    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
+    const unsigned long long i0 = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
+    const unsigned long long lo = b.first, hi = (unsigned long long)b.first + b.n;
+    const double half_dt = __dmul_rn(0.5, dt);
+    // pass 1: kinetic energy of v1 = v + dt/2 f/m, nothing written
+        {
+        Acc a;
+        acc_zero(a);
+        double ke0 = 0.0, ke1 = 0.0;
+        unsigned long long i = i0;
+        for (; i + stride < N; i += 2 * stride)
+            {
+            const double4 va = ld256_na(vel + i), vb = ld256_na(vel + i + stride);
+            const double ca = __ldg(r1.charge + i), cb = __ldg(r1.charge + i + stride);
+            double4 fa = force_of(i, ca, s_fin, r1.f), fb = force_of(i + stride, cb, s_fin, r1.f);
+            if (force_other)
+                {
+                const double4 oa = ld256(force_other + i), ob = ld256(force_other + i + stride);
+                fa.x = __dadd_rn(oa.x, fa.x); fa.y = __dadd_rn(oa.y, fa.y); fa.z = __dadd_rn(oa.z, fa.z);
+                fb.x = __dadd_rn(ob.x, fb.x); fb.y = __dadd_rn(ob.y, fb.y); fb.z = __dadd_rn(ob.z, fb.z);
+                }
+            const double ha = __ddiv_rn(half_dt, va.w), hb = __ddiv_rn(half_dt, vb.w);
+            const double ax = __dadd_rn(va.x, __dmul_rn(ha, fa.x)), ay = __dadd_rn(va.y, __dmul_rn(ha, fa.y)),
+                         az = __dadd_rn(va.z, __dmul_rn(ha, fa.z));
+            const double bx = __dadd_rn(vb.x, __dmul_rn(hb, fb.x)), by = __dadd_rn(vb.y, __dmul_rn(hb, fb.y)),
+                         bz = __dadd_rn(vb.z, __dmul_rn(hb, fb.z));
+            if (i >= lo && i < hi)
+                ke0 += va.w * (ax * ax + ay * ay + az * az);
+            if (i + stride >= lo && i + stride < hi)
+                ke1 += vb.w * (bx * bx + by * by + bz * bz);
+            }
+        for (; i < N; i += stride)
+            {
+            const double4 va = ld256_na(vel + i);
+            double4 fa = force_of(i, __ldg(r1.charge + i), s_fin, r1.f);
+            if (force_other)
+                {
+                const double4 oa = ld256(force_other + i);
+                fa.x = __dadd_rn(oa.x, fa.x); fa.y = __dadd_rn(oa.y, fa.y); fa.z = __dadd_rn(oa.z, fa.z);
+                }
+            const double ha = __ddiv_rn(half_dt, va.w);
+            const double ax = __dadd_rn(va.x, __dmul_rn(ha, fa.x)), ay = __dadd_rn(va.y, __dmul_rn(ha, fa.y)),
+                         az = __dadd_rn(va.z, __dmul_rn(ha, fa.z));
+            if (i >= lo && i < hi)
+                ke0 += va.w * (ax * ax + ay * ay + az * az);
+            }
+        a.ke = ke0 + ke1;
+        block_merge<false, true>(a, fnew, sc);
+        }
+    if (threadIdx.x == 0)
+        publish_record(recsB + g.blk, sc.rec, epoch);
+    // (pulling this thread's pass-2 positions and images into L2 with prefetch.global.L2 while alpha is awaited was
+    // measured: no gain at 1M, 130.4 -> 133.9 us at 4M where it evicts the velocities; not done)
+    const Final finK = take_final<false>(finals + 1, epoch, prefetch_final<false>(finals + 1));
+    if (finK.timeout)
+        return;
+    const double alpha = (b.rescale && finK.bussi_ok) ? finK.alpha : 1.0;
+    // pass 2: v2 = alpha v1 + dt/2 f/m, r += dt v2, dipole term of the new position (U2 particles in flight per thread)
+    Acc a;
+    acc_zero(a);
+    auto finish = [&](unsigned long long i, double4 v, double4 p, double c, int ix, int iy, int iz, double4 f)
+        {
+        const double hm = __ddiv_rn(half_dt, v.w);
+        v.x = __dadd_rn(v.x, __dmul_rn(hm, f.x));
+        v.y = __dadd_rn(v.y, __dmul_rn(hm, f.y));
+        v.z = __dadd_rn(v.z, __dmul_rn(hm, f.z));
+        if (i >= lo && i < hi)
+            {
+            v.x = __dmul_rn(v.x, alpha);
+            v.y = __dmul_rn(v.y, alpha);
+            v.z = __dmul_rn(v.z, alpha);
+            }
+        v.x = __dadd_rn(v.x, __dmul_rn(hm, f.x));
+        v.y = __dadd_rn(v.y, __dmul_rn(hm, f.y));
+        v.z = __dadd_rn(v.z, __dmul_rn(hm, f.z));
+        p.x = __dadd_rn(p.x, __dmul_rn(dt, v.x));
+        p.y = __dadd_rn(p.y, __dmul_rn(dt, v.y));
+        p.z = __dadd_rn(p.z, __dmul_rn(dt, v.z));
+        st256(vel + i, v);
+        st256(pos + i, p);
+        take_particle(a, (unsigned int)i, p, c, ix, iy, iz, fnew);
+        };
+    unsigned long long i = i0;
+    for (; i + (U2 - 1) * stride < N; i += U2 * stride)
+        {
+        double4 v[U2], p[U2], f[U2];
+        double c[U2];
+        int ix[U2], iy[U2], iz[U2];
+#pragma unroll
+        for (int k = 0; k < U2; k++)
+            {
+            const unsigned long long j = i + k * stride;
+            v[k] = ld256(vel + j);
+            p[k] = ld256_stream(pos + j);
+            c[k] = __ldg(r1.charge + j);
+            ix[k] = __ldg(fnew.image + 3 * j + 0);
+            iy[k] = __ldg(fnew.image + 3 * j + 1);
+            iz[k] = __ldg(fnew.image + 3 * j + 2);
+            if (force_other)
+                f[k] = ld256(force_other + j);
+            }
+#pragma unroll
+        for (int k = 0; k < U2; k++)
+            {
+            const unsigned long long j = i + k * stride;
+            double4 fc = force_of(j, c[k], s_fin, r1.f);
+            if (force_other)
+                {
+                fc.x = __dadd_rn(f[k].x, fc.x);
+                fc.y = __dadd_rn(f[k].y, fc.y);
+                fc.z = __dadd_rn(f[k].z, fc.z);
+                }
+            finish(j, v[k], p[k], c[k], ix[k], iy[k], iz[k], fc);
+            }
+        }
+    for (; i < N; i += stride)
+        {
+        const double c = __ldg(r1.charge + i);
+        double4 fc = force_of(i, c, s_fin, r1.f);
+        if (force_other)
+            {
+            const double4 fo = ld256(force_other + i);
+            fc.x = __dadd_rn(fo.x, fc.x);
+            fc.y = __dadd_rn(fo.y, fc.y);
+            fc.z = __dadd_rn(fo.z, fc.z);
+            }
+        finish(i, ld256(vel + i), ld256_stream(pos + i), c, __ldg(fnew.image + 3 * i + 0), __ldg(fnew.image + 3 * i + 1),
+               __ldg(fnew.image + 3 * i + 2), fc);
+        }
+    block_merge<true, false>(a, fnew, sc);
+    if (threadIdx.x == 0)
+        publish_record(recsF + g.blk, sc.rec, epoch);
+    pdl_launch_dependents();
+    }
+
 template<bool DRIFT>
 __global__ void __launch_bounds__(256) k_nve(double4* pos, double4* vel, const double4* force, uint32_t N, double dt)
     {
@@ -490,6 +676,94 @@ extern "C" int cavb200_md_step_one(cavb200_handle* h, double* pos, double* vel, 
                                                       h->scalars, r, fnew, h->partials, h->counters + 4,
                                                       const_cast<Final*>(rank1_final(h)));
     CAVB_CHECK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+    }
+
+extern "C" int cavb200_md_step_fused(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                                     const double* charge, const int32_t* image, uint32_t N, double dt, double Lx,
+                                     double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params,
+                                     uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    if (!pos || !vel || !charge || !image || !params || (unsigned long long)group_first + n_group > N)
+        return (int)cudaErrorInvalidValue;
+    if (mis32(pos) || mis32(vel) || mis32(force_other) || (reinterpret_cast<uintptr_t>(image) & 3))
+        return (int)cudaErrorMisalignedAddress;
+    if (!h->coop_supported)
+        return (int)cudaErrorNotSupported;
+    Rank1In r;
+    int rc = fill_rank1(h, r, charge, pos, L_typeid, params->couplstr);
+    if (rc)
+        return rc;
+    ForceIn fnew = {};
+    fnew.pos = reinterpret_cast<const double4*>(pos);
+    fnew.charge = charge;
+    fnew.image = image;
+    fnew.N = N;
+    fnew.Lx = Lx;
+    fnew.Ly = Ly;
+    fnew.Lz = Lz;
+    fnew.L_typeid = L_typeid;
+    fnew.g = params->couplstr;
+    fnew.K = params->K;
+    fill_force_constants(fnew);
+    BussiIn b = {};
+    b.first = group_first;
+    b.n = n_group;
+    b.rescale = bussi != nullptr && bussi->deltaT != 0.0;
+    if (bussi)
+        fill_bussi_constants(b, bussi);
+    const void* kern;
+    int threads, per_sm_want;
+    switch (h->tune.md_shape)
+        {
+    case 1:  kern = (const void*)k_md_fused<384, 1>; threads = 384; per_sm_want = 2; break;
+    default: kern = (const void*)k_md_fused<768, 1>; threads = 768; per_sm_want = 1; break; // folder CTA alone on its SM
+        }
+    int per_sm = 0;
+    CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+    if (per_sm < 1)
+        return (int)cudaErrorLaunchOutOfResources;
+    if (per_sm > per_sm_want)
+        per_sm = per_sm_want;
+    int max_grid = per_sm * h->num_sms;
+    if (max_grid > MAX_PARTIALS / 4 - 2)
+        max_grid = MAX_PARTIALS / 4 - 2;
+    const unsigned long long want = ((unsigned long long)N + threads - 1) / threads;
+    // the CTAs wait on each other: the grid must be co-resident; one of them folds instead of streaming
+    const int grid = (int)(want < (unsigned long long)(max_grid - 1) ? want : (unsigned long long)(max_grid - 1)) + 1;
+    double4* p4 = (double4*)pos;
+    double4* v4 = (double4*)vel;
+    const double4* fo4 = (const double4*)force_other;
+    Partial* recsF = h->partials;
+    Partial* recsB = h->partials + MAX_PARTIALS / 2;
+    Partial* finals = h->partials + MAX_PARTIALS - 2;
+    Scalars* sca = h->scalars;
+    unsigned long long* ctr = h->counters + 2;
+    Final* fin_out = const_cast<Final*>(rank1_final(h));
+    void* args[] = {&p4, &v4, &fo4, &N, &dt, &b, &r, &fnew, &recsF, &recsB, &finals, &sca, &ctr, &fin_out};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr;
+    if (h->tune.pdl)
+        {
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        }
+    else
+        {
+        attr.id = cudaLaunchAttributeCooperative;
+        attr.val.cooperative = 1;
+        }
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    CAVB_CHECK(cudaLaunchKernelExC(&cfg, kern, args));
     h->launches += 1;
     return 0;
     }

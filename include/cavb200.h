@@ -197,6 +197,16 @@ int cavb200_md_step_one(cavb200_handle* h, double* pos, double* vel, const doubl
                         const int32_t* image, uint32_t N, double dt, double Lx, double Ly, double Lz, uint32_t L_typeid,
                         const cavb200_params* params, uint32_t group_first, uint32_t n_group,
                         const cavb200_bussi_args* bussi, void* stream);
+/*   cavb200_md_step_fused    ONE launch per MD step: cavb200_nvt_step_two_rank1 of the previous step followed by
+ *                            cavb200_md_step_one of this step (second half kick, KE, alpha, rescale, first half kick,
+ *                            drift, dipole reduce of the new positions), every array moved once: 148 B/particle.
+ *                            A run is  cavb200_force_rank1 ; cavb200_bussi_ke ; cavb200_md_step_one ;
+ *                            cavb200_md_step_fused x (T-1) ; cavb200_nvt_step_two_rank1.
+ *                            `bussi` holds the draws of the step whose first half it performs. */
+int cavb200_md_step_fused(cavb200_handle* h, double* pos, double* vel, const double* force_other, const double* charge,
+                          const int32_t* image, uint32_t N, double dt, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                          const cavb200_params* params, uint32_t group_first, uint32_t n_group,
+                          const cavb200_bussi_args* bussi, void* stream);
 int cavb200_nvt_step_two_rank1(cavb200_handle* h, double* vel, const double* force_other, const double* charge,
                                const double* pos, uint32_t N, double dt, uint32_t L_typeid, double couplstr,
                                uint32_t group_first, uint32_t n_group, void* stream);

@@ -100,6 +100,10 @@ def test_guards_harness_steps(handle, n_mol):
     handle.force_rank1(P["pos"], P["charge"], P["image"], s.N, s.box, s.L_typeid, p)
     handle.nvt_step_one_rank1(P["pos"], P["vel"], P["net"], P["charge"], s.N, 1.0, s.L_typeid, 1e-3, 0, n_mol, a)
     handle.md_step_one(P["pos"], P["vel"], None, P["charge"], P["image"], s.N, 1.0, s.box, s.L_typeid, p, 0, n_mol, a)
+    for shape in (0, 1):
+        handle.set_tuning(md_shape=shape)
+        handle.md_step_fused(P["pos"], P["vel"], P["net"], P["charge"], P["image"], s.N, 1.0, s.box, s.L_typeid, p, 0, n_mol, a)
+    handle.set_tuning(md_shape=0)
     handle.nvt_step_two_rank1(P["vel"], P["net"], P["charge"], P["pos"], s.N, 1.0, s.L_typeid, 1e-3, 0, n_mol)
     handle.track_open(4)
     handle.track_set_reference()

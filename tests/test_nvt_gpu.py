@@ -294,3 +294,88 @@ def test_md_step_one_argument_errors(handle):
     with pytest.raises(capi.CavbError):
         handle.md_step_one(a, a, None, None, a, 8, 1.0, (1.0, 1.0, 1.0), 2, p, 0, 8)
     handle.md_step_one(None, None, None, None, None, 0, 1.0, (1.0, 1.0, 1.0), 2, p, 0, 0)  # N == 0: no-op
+
+
+# ---- one launch per MD step (cavb200_md_step_fused) --------------------------------------------------
+@pytest.mark.parametrize("photon", ["last", "middle", "duplicated", "absent"])
+@pytest.mark.parametrize("n_mol", [1, 300, 20000, 200000])
+def test_md_step_fused_matches_two_launch_path_and_oracle(handle, coracle, n_mol, photon):
+    """md_step_one ; md_step_fused x (T-1) ; nvt_step_two_rank1  ==  (md_step_one ; nvt_step_two_rank1) x T  (<= 1e-13: the
+    kinetic energy is summed over another partition of the particles)  ==  orc_nvt_step x T (tolerances as above)."""
+    steps, dt = 8, synth.DT_1FS
+    s = synth.make_system(n_mol, replica=17, photon=photon)
+    first, n = (0, n_mol) if photon in ("last", "absent") else (0, s.N)
+    dof = max(3.0 * n - 3.0, 1.0)
+    p = capi.Params.make(OMEGAC, G, PHMASS)
+    st = capi.Stream()
+    draws = [rng.bussi_draws(t, 9, 0, dof) for t in range(steps)]
+
+    def run(fused):
+        d = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+        handle.bussi_reset(st.ptr)
+        handle.force_rank1(d["pos"], d["charge"], d["image"], s.N, s.box, s.L_typeid, p, st.ptr)
+        handle.bussi_ke(d["vel"], None, first, n, st.ptr)
+        alphas = []
+        for t in range(steps):
+            a = capi.BussiArgs(synth.KT_100K, synth.TAU_5PS, dt, dof, *draws[t])
+            if fused and t > 0:
+                handle.md_step_fused(d["pos"], d["vel"], None, d["charge"], d["image"], s.N, dt, s.box, s.L_typeid, p, first, n,
+                                     a, st.ptr)
+            else:
+                handle.md_step_one(d["pos"], d["vel"], None, d["charge"], d["image"], s.N, dt, s.box, s.L_typeid, p, first, n,
+                                   a, st.ptr)
+            alphas.append(handle.bussi_read(st.ptr)["alpha"])
+            if not fused or t == steps - 1:
+                handle.nvt_step_two_rank1(d["vel"], None, d["charge"], d["pos"], s.N, dt, s.L_typeid, G, first, n, st.ptr)
+        b = handle.bussi_read(st.ptr)
+        en, dip, ph = handle.force_read(st.ptr)
+        return d["pos"].numpy(st.ptr), d["vel"].numpy(st.ptr), alphas, b, en, ph
+
+    pa, va, aa, ba, ena, pha = run(False)
+    pb, vb, ab, bb, enb, phb = run(True)
+    assert pha == phb and bb["err"] == 0.0
+    assert _rel(pb[:, :3], pa[:, :3]) <= 1e-13 and _rel(vb[:, :3], va[:, :3]) <= 1e-13
+    assert np.allclose(aa, ab, rtol=1e-13, atol=0) and abs(ba["ke"] - bb["ke"]) <= 1e-12 * ba["ke"]
+    assert abs(ba["cumulative"] - bb["cumulative"]) <= 1e-12 * max(abs(ba["ke"]), 1e-300)
+    assert np.allclose(ena, enb, rtol=1e-12, atol=1e-300)
+    # oracle
+    pos, vel, force = s.pos.copy(), s.vel.copy(), np.zeros((s.N, 4))
+    force[:] = coracle.cavity_force(pos, s.charge, s.image, s.box, s.L_typeid, OMEGAC, G, PHMASS)["force"]
+    idx = np.arange(first, first + n, dtype=np.uint32)
+    ke = np.array([coracle.kinetic_energy(vel, idx)])
+    res = np.zeros(2)
+    for t in range(steps):
+        a_ref, en_ref = coracle.nvt_step(pos, vel, s.charge, s.image, force, s.box, s.L_typeid, OMEGAC, G, PHMASS, dt, first, n,
+                                         dof, synth.KT_100K, synth.TAU_5PS, draws[t][0], draws[t][1], res, ke)
+        assert abs(ab[t] - a_ref) <= 1e-12 * abs(a_ref)
+    assert _rel(pb[:, :3], pos[:, :3]) <= 1e-10 and _rel(vb[:, :3], vel[:, :3]) <= 1e-10
+    assert abs(bb["ke"] - ke[0]) <= 1e-10 * ke[0] and np.allclose(enb, en_ref, rtol=1e-10, atol=1e-300)
+    assert np.array_equal(pb[:, 3].view(np.uint64), s.pos[:, 3].view(np.uint64)) and np.array_equal(vb[:, 3], s.vel[:, 3])
+
+
+def test_md_step_fused_windowed_group_and_other_forces(handle):
+    """Thermostatted window + an `other forces` array: fused launch == the two-launch path."""
+    n_mol, dt = 30000, 5.0
+    s = synth.make_system(n_mol, replica=23)
+    first, n = 1000, 20000
+    dof = 3.0 * n - 3.0
+    p = capi.Params.make(OMEGAC, G, PHMASS)
+    other = np.random.default_rng(5).normal(size=(s.N, 4)) * 1e-5
+    outs = []
+    for fused in (False, True):
+        d = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+        d_o = capi.DeviceArray.from_numpy(other)
+        handle.bussi_reset()
+        handle.force_rank1(d["pos"], d["charge"], d["image"], s.N, s.box, s.L_typeid, p)
+        handle.bussi_ke(d["vel"], None, first, n)
+        for t in range(4):
+            a = capi.BussiArgs(synth.KT_100K, synth.TAU_5PS, dt, dof, *rng.bussi_draws(t, 2, 0, dof))
+            if fused and t > 0:
+                handle.md_step_fused(d["pos"], d["vel"], d_o, d["charge"], d["image"], s.N, dt, s.box, s.L_typeid, p, first, n, a)
+            else:
+                handle.md_step_one(d["pos"], d["vel"], d_o, d["charge"], d["image"], s.N, dt, s.box, s.L_typeid, p, first, n, a)
+            if not fused or t == 3:
+                handle.nvt_step_two_rank1(d["vel"], d_o, d["charge"], d["pos"], s.N, dt, s.L_typeid, G, first, n)
+        outs.append((d["pos"].numpy(), d["vel"].numpy(), handle.bussi_read()))
+    assert _rel(outs[1][0][:, :3], outs[0][0][:, :3]) <= 1e-13 and _rel(outs[1][1][:, :3], outs[0][1][:, :3]) <= 1e-13
+    assert abs(outs[1][2]["alpha"] - outs[0][2]["alpha"]) <= 1e-13

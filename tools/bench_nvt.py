@@ -6,6 +6,7 @@ Compares, per MD step at N particles, rotating over systems larger than L2:
   B  nvt_step_one ; force ; nvt_step_two                      (thermostat folded in:        340 B/particle)
   C  nvt_step_one_rank1 ; force_rank1 ; nvt_step_two_rank1    (8f.2, force never written:   260 B/particle)
   D  md_step_one ; nvt_step_two_rank1                         (next dipole reduce inside step one: 220 B/particle, 2 launches)
+  E  md_step_fused                                            (step two of t-1 + step one of t in ONE launch: 148 B/particle)
 Algorithmic bytes: kick+drift 160 (vel, force, pos in; vel, pos out), force 84, half kick 96, Bussi 64;
 rank-1: kick+drift reading charge instead of force 136, dipole reduce 52, half kick 72."""
 import argparse
@@ -60,10 +61,13 @@ def main():
                 h.nvt_step_one_rank1(d["pos"], d["vel"], None, d["charge"], N, dt, base.L_typeid, 1e-3, 0, n_mol, a, st.ptr)
                 h.force_rank1(d["pos"], d["charge"], d["image"], N, base.box, base.L_typeid, p, st.ptr)
                 h.nvt_step_two_rank1(d["vel"], None, d["charge"], d["pos"], N, dt, base.L_typeid, 1e-3, 0, n_mol, st.ptr)
-            else:
+            elif kind == "D":
                 h.md_step_one(d["pos"], d["vel"], None, d["charge"], d["image"], N, dt, base.box, base.L_typeid, p, 0, n_mol,
                               a, st.ptr)
                 h.nvt_step_two_rank1(d["vel"], None, d["charge"], d["pos"], N, dt, base.L_typeid, 1e-3, 0, n_mol, st.ptr)
+            else:
+                h.md_step_fused(d["pos"], d["vel"], None, d["charge"], d["image"], N, dt, base.box, base.L_typeid, p, 0, n_mol,
+                                a, st.ptr)
 
         def run(kind, steps):
             e0, e1 = capi.Event(), capi.Event()
@@ -75,7 +79,7 @@ def main():
             return e1.elapsed_ms_since(e0) / steps
 
         kinds = [("A", 404), ("B", 340)]
-        kinds += [("C", 260), ("D", 220)]
+        kinds += [("C", 260), ("D", 220), ("E", 148)]
         print(f"N={N} systems={n_sys} peak={peak} GB/s")
         for kind, nbytes in kinds:
             run(kind, 5)

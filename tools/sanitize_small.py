@@ -40,6 +40,7 @@ def main():
         h.net_force_add_rank1(d_net, dev["charge"], dev["pos"], s.N, s.L_typeid, 1e-3)
         h.nvt_step_one_rank1(dev["pos"], dev["vel"], d_net, dev["charge"], s.N, 1.0, s.L_typeid, 1e-3, 0, n_mol, a)
         h.md_step_one(dev["pos"], dev["vel"], None, dev["charge"], dev["image"], s.N, 1.0, s.box, s.L_typeid, p, 0, n_mol, a)
+        h.md_step_fused(dev["pos"], dev["vel"], d_net, dev["charge"], dev["image"], s.N, 1.0, s.box, s.L_typeid, p, 0, n_mol, a)
         h.nvt_step_two_rank1(dev["vel"], d_net, dev["charge"], dev["pos"], s.N, 1.0, s.L_typeid, 1e-3, 0, n_mol)
         h.track_open(3)
         h.track_set_reference()
