@@ -1124,7 +1124,7 @@ template<bool FORCE> __device__ __forceinline__ FinalSectors prefetch_final(cons
         }
     return r;
     }
-template<bool FORCE>
+template<bool FORCE, int POLL_NS = CAVB_FINAL_POLL_NS>
 __device__ __forceinline__ Final take_final(const Partial* src, unsigned long long epoch, const FinalSectors& pre)
     {
     const double4* p = reinterpret_cast<const double4*>(src);
@@ -1135,13 +1135,13 @@ __device__ __forceinline__ Final take_final(const Partial* src, unsigned long lo
     fin.photon_local = -1;
     double4 s0 = pre.s0, s1 = pre.s1, s2 = pre.s2;
     if (!sector_ok(s2, epoch))
-        s2 = read_sector<true, false, CAVB_FINAL_POLL_NS>(p + 2, epoch, late);
+        s2 = read_sector<true, false, POLL_NS>(p + 2, epoch, late);
     if (FORCE)
         {
         if (!sector_ok(s0, epoch))
-            s0 = read_sector<true, false, CAVB_FINAL_POLL_NS>(p + 0, epoch, late);
+            s0 = read_sector<true, false, POLL_NS>(p + 0, epoch, late);
         if (!sector_ok(s1, epoch))
-            s1 = read_sector<true, false, CAVB_FINAL_POLL_NS>(p + 1, epoch, late);
+            s1 = read_sector<true, false, POLL_NS>(p + 1, epoch, late);
         fin.Dq[0] = s0.x;
         fin.Dq[1] = s0.y;
         fin.FL[0] = s0.z;
