@@ -51,3 +51,44 @@ def test_nve_drift_no_worse_than_oracle(handle, coracle, dt):
     # same integrator arithmetic on both arms: the trajectories stay together
     assert np.abs(E_gpu - E_cpu).max() <= 1e-9 * abs(E_cpu[0])
     assert np.allclose(d["pos"].numpy(st.ptr)[:, :3], pos[:, :3], rtol=1e-8, atol=1e-8)
+
+
+def test_nve_drift_one_launch_per_step(handle, coracle):
+    """The same 10k-step NVE comparison through the most fused path: cavb200_md_step_fused with no thermostat
+    (alpha = 1), i.e. ONE persistent launch per MD step with the rank-1 cavity force never stored."""
+    n_mol, steps, every, dt = 2000, 10000, 500, 5.0
+    omegac, g, phmass = 0.01, 1e-3, 1.0
+    s = synth.make_system(n_mol, images=False)
+    pos, vel, force = s.pos.copy(), s.vel.copy(), np.zeros((s.N, 4))
+    e = coracle.cavity_force(pos, s.charge, s.image, s.box, s.L_typeid, omegac, g, phmass)
+    force[:] = e["force"]
+    E_cpu = [total_energy(vel, e["energies"])]
+    for k in range(steps):
+        en = coracle.nve_step(pos, vel, s.charge, s.image, force, s.box, s.L_typeid, omegac, g, phmass, dt)
+        if (k + 1) % every == 0:
+            E_cpu.append(total_energy(vel, en))
+    d = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+    p = capi.Params.make(omegac, g, phmass)
+    st = capi.Stream()
+    handle.force_rank1(d["pos"], d["charge"], d["image"], s.N, s.box, s.L_typeid, p, st.ptr)
+    E_gpu = [total_energy(d["vel"].numpy(st.ptr), handle.force_read(st.ptr)[0])]
+    handle.md_step_one(d["pos"], d["vel"], None, d["charge"], d["image"], s.N, dt, s.box, s.L_typeid, p, 0, 0, None, st.ptr)
+    for k in range(steps):
+        if (k + 1) % every == 0 or k == steps - 1:
+            # close the step (second half kick) on a copy of the velocities to read the energy at a whole step
+            v_copy = capi.DeviceArray.from_numpy(d["vel"].numpy(st.ptr))
+            handle.nvt_step_two_rank1(v_copy, None, d["charge"], d["pos"], s.N, dt, s.L_typeid, g, 0, 0, st.ptr)
+            E_gpu.append(total_energy(v_copy.numpy(st.ptr), handle.force_read(st.ptr)[0]))
+            v_last = v_copy
+        if k < steps - 1:
+            handle.md_step_fused(d["pos"], d["vel"], None, d["charge"], d["image"], s.N, dt, s.box, s.L_typeid, p, 0, 0, None,
+                                 st.ptr)
+    E_cpu, E_gpu = np.array(E_cpu), np.array(E_gpu)
+    drift_cpu = np.abs(E_cpu - E_cpu[0]).max() / abs(E_cpu[0])
+    drift_gpu = np.abs(E_gpu - E_gpu[0]).max() / abs(E_gpu[0])
+    print(f"NVE 10k steps, one launch per step: relative drift cpu {drift_cpu:.3e} gpu {drift_gpu:.3e}")
+    assert len(E_gpu) == len(E_cpu)
+    assert drift_gpu <= 1.02 * drift_cpu + 1e-12
+    assert np.abs(E_gpu - E_cpu).max() <= 1e-9 * abs(E_cpu[0])
+    assert np.allclose(d["pos"].numpy(st.ptr)[:, :3], pos[:, :3], rtol=1e-8, atol=1e-8)
+    assert np.allclose(v_last.numpy(st.ptr)[:, :3], vel[:, :3], rtol=1e-7, atol=1e-12)
