@@ -379,3 +379,57 @@ def test_md_step_fused_windowed_group_and_other_forces(handle):
         outs.append((d["pos"].numpy(), d["vel"].numpy(), handle.bussi_read()))
     assert _rel(outs[1][0][:, :3], outs[0][0][:, :3]) <= 1e-13 and _rel(outs[1][1][:, :3], outs[0][1][:, :3]) <= 1e-13
     assert abs(outs[1][2]["alpha"] - outs[0][2]["alpha"]) <= 1e-13
+
+
+def test_bussi_conserved_quantity_one_launch_per_step(handle, coracle):
+    """Bussi's conserved quantity: system energy + energy handed to the reservoir (the cumulative KE (1 - alpha^2) of
+    reference src/BussiReservoirThermostat.h:86-95) stays constant up to the integrator's own error.  2000 thermostatted
+    steps through cavb200_md_step_fused; the same run through the oracle gives the yardstick."""
+    n_mol, steps, dt = 2000, 2000, 5.0
+    s = synth.make_system(n_mol, replica=31, images=False)
+    dof = 3.0 * n_mol - 3.0
+    kT, tau = synth.KT_100K, 200.0  # strong coupling so that the reservoir term is large
+    p = capi.Params.make(OMEGAC, G, PHMASS)
+    draws = [rng.bussi_draws(t, 4, 0, dof) for t in range(steps)]
+
+    def total(vel, en):
+        return 0.5 * np.sum(vel[:, 3] * np.sum(vel[:, :3] ** 2, axis=1)) + en.sum()
+
+    # oracle
+    pos, vel, force = s.pos.copy(), s.vel.copy(), np.zeros((s.N, 4))
+    e0 = coracle.cavity_force(pos, s.charge, s.image, s.box, s.L_typeid, OMEGAC, G, PHMASS)
+    force[:] = e0["force"]
+    ke = np.array([coracle.kinetic_energy(vel, np.arange(n_mol, dtype=np.uint32))])
+    res = np.zeros(2)
+    H_cpu = [total(vel, e0["energies"])]
+    for t in range(steps):
+        _, en = coracle.nvt_step(pos, vel, s.charge, s.image, force, s.box, s.L_typeid, OMEGAC, G, PHMASS, dt, 0, n_mol, dof, kT,
+                                 tau, draws[t][0], draws[t][1], res, ke)
+        if (t + 1) % 200 == 0:
+            H_cpu.append(total(vel, en) + res[0])
+    # GPU, one launch per step
+    st = capi.Stream()
+    d = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+    handle.bussi_reset(st.ptr)
+    handle.force_rank1(d["pos"], d["charge"], d["image"], s.N, s.box, s.L_typeid, p, st.ptr)
+    handle.bussi_ke(d["vel"], None, 0, n_mol, st.ptr)
+    H_gpu = [total(s.vel, handle.force_read(st.ptr)[0])]
+    for t in range(steps):
+        a = capi.BussiArgs(kT, tau, dt, dof, *draws[t])
+        if t == 0:
+            handle.md_step_one(d["pos"], d["vel"], None, d["charge"], d["image"], s.N, dt, s.box, s.L_typeid, p, 0, n_mol, a, st.ptr)
+        else:
+            handle.md_step_fused(d["pos"], d["vel"], None, d["charge"], d["image"], s.N, dt, s.box, s.L_typeid, p, 0, n_mol, a,
+                                 st.ptr)
+        if (t + 1) % 200 == 0:
+            v_copy = capi.DeviceArray.from_numpy(d["vel"].numpy(st.ptr))
+            handle.nvt_step_two_rank1(v_copy, None, d["charge"], d["pos"], s.N, dt, s.L_typeid, G, 0, n_mol, st.ptr)
+            b = handle.bussi_read(st.ptr)
+            H_gpu.append(total(v_copy.numpy(st.ptr), handle.force_read(st.ptr)[0]) + b["cumulative"])
+    H_cpu, H_gpu = np.array(H_cpu), np.array(H_gpu)
+    dev_cpu = np.abs(H_cpu - H_cpu[0]).max() / abs(H_cpu[0])
+    dev_gpu = np.abs(H_gpu - H_gpu[0]).max() / abs(H_gpu[0])
+    print(f"Bussi conserved quantity over {steps} steps: relative deviation cpu {dev_cpu:.3e} gpu {dev_gpu:.3e}; reservoir {res[0]:.4e}")
+    assert abs(res[0]) > 1e-3 * abs(H_cpu[0])          # the thermostat really exchanged energy
+    assert dev_gpu <= 1.05 * dev_cpu + 1e-12
+    assert np.abs(H_gpu - H_cpu).max() <= 1e-8 * abs(H_cpu[0])
