@@ -529,7 +529,7 @@ def run_b200(args):
                             f"; {world} independent replicas, one per GPU (configs[2])" if world > 1 else ""),
             "path": "cavb200_step: cavity force + Bussi thermostat in one launch (split-phase kernel with a folder CTA), device-resident arrays",
             "l2": f"inputs larger than L2: rotating over {len(systems)} systems x {116 * N / 1e6:.0f} MB",
-            "tuning": {k: h.get_tuning(k) for k in ("variant", "threads", "ctas_per_sm", "unroll", "pdl")},
+            "tuning": {k: h.get_tuning(k) for k in ("variant", "threads", "auto_threads", "ctas_per_sm", "unroll", "pdl")},
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -135,6 +135,7 @@ int cavb200_create(cavb200_handle** out, int device)
     h->tune.ctas_per_sm = 2;
     h->tune.unroll = 2;
     h->tune.pdl = 1;
+    h->tune.auto_threads = 1;
     h->tune.rhok_threads = 256;
     h->tune.rhok_kblock = 8;
     h->shard.mode = 0;
@@ -181,6 +182,7 @@ static int* tuning_slot(cavb::Tuning* t, const char* key)
     if (!strcmp(key, "rhok_threads")) return &t->rhok_threads;
     if (!strcmp(key, "rhok_kblock")) return &t->rhok_kblock;
     if (!strcmp(key, "ke_first")) return &t->ke_first;
+    if (!strcmp(key, "auto_threads")) return &t->auto_threads;
     if (!strcmp(key, "md_shape")) return &t->md_shape;
     return nullptr;
     }
@@ -199,6 +201,8 @@ int cavb200_set_tuning(cavb200_handle* h, const char* key, int value)
     if (!strcmp(key, "unroll") && value != 2 && value != 4 && value != 8)
         return (int)cudaErrorInvalidValue;
     *slot = value;
+    if (!strcmp(key, "threads"))
+        h->tune.auto_threads = 0; // an explicit CTA size switches the automatic choice off (set auto_threads = 1 to re-enable)
     return 0;
     }
 

@@ -168,3 +168,20 @@ def test_step_full_sizes(handle, coracle, n_mol):
     assert abs(ke1 - bo["alpha"] ** 2 * ke0) <= 1e-12 * ke0
     assert np.array_equal(v[:, 3], s.vel[:, 3])
     assert np.array_equal(v[n_mol], s.vel[n_mol])  # the photon is outside the thermostatted group
+
+
+@pytest.mark.parametrize("n_mol", [262145, 500000, 1_000_000])
+def test_step_automatic_cta_size(handle, coracle, n_mol):
+    """Default tuning: the step kernel picks 320 / 352 / 384 threads per CTA from the particle count
+    (fewest dependent memory round trips per pass); an explicit `threads` switches that off.  Parity either way."""
+    s = synth.make_system(n_mol, replica=2)
+    a = args_for(n_mol)
+    h2 = capi.Handle(0)   # fresh handle: defaults
+    try:
+        assert h2.get_tuning("auto_threads") == 1 and h2.get_tuning("variant") == 3
+        check_against_oracle(coracle, s, 0, n_mol, a, run_step(h2, s, 0, n_mol, a))
+        h2.set_tuning(threads=384)
+        assert h2.get_tuning("auto_threads") == 0
+        check_against_oracle(coracle, s, 0, n_mol, a, run_step(h2, s, 0, n_mol, a))
+    finally:
+        h2.close()
