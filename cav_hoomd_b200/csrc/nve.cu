@@ -1,12 +1,14 @@
-// nve.cu -- minimal velocity-Verlet harness around the cavity force (energy-drift comparison).
-// Same arithmetic as oracle/cavity_oracle.c orc_nve_step: hm = 0.5*dt/m; v = v + hm*f; r = r + dt*v,
-// each product and sum rounded separately (no FMA) so that both arms integrate identically.
-//
-// Thermostatted variant (cavb200_nvt_step_one / _two): the Bussi rescale rides on the
-// first half step and the kinetic energy the thermostat needs at the NEXT step is accumulated while the
-// second half step writes the velocities, so the thermostat costs no pass of its own (the standalone
-// cavb200_bussi call moves 64 B/particle, 96 B once the velocities no longer fit L2).  Same arithmetic
-// as oracle/cavity_oracle.c orc_nvt_step.  This is the repo's own harness, NOT HOOMD's integrator.
+// nve.cu -- the repo's own velocity-Verlet harness around the cavity force (NOT HOOMD's integrator; HOOMD's
+// TwoStepConstantVolume is upstream code that is not in the reference tree).  Everything here uses the arithmetic of
+// oracle/cavity_oracle.c orc_nve_step / orc_nvt_step: hm = 0.5*dt/m; v = v + hm*f; r = r + dt*v, each product and sum
+// rounded separately (no FMA) so that both arms integrate identically.  In order of increasing fusion:
+//   k_nve<DRIFT>            cavb200_nve_kick_drift / _half_kick: plain NVE steps (energy-drift comparison)
+//   k_nvt_one / k_nvt_two   SURVEY.md 8f.1: the Bussi rescale rides on the first half step, the kinetic energy for the
+//                           NEXT step is summed while the second half step writes the velocities (no thermostat pass)
+//   ... <RANK1>             SURVEY.md 8f.2: the cavity force is never stored, F_i = (-g c_i) Dq is formed in the kick
+//   k_net_force_add_rank1   what a net-force sum does with that rank-1 contribution
+//   k_md_one                step one with the NEXT force's dipole reduce inside (positions read once)
+//   k_md_fused              step two of step t-1 + step one of step t in ONE persistent launch (148 B/particle)
 #include "hotpath.cuh"
 
 namespace cavb
