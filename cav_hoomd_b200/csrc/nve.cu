@@ -11,6 +11,10 @@
 //   k_md_fused              step two of step t-1 + step one of step t in ONE persistent launch (148 B/particle)
 #include "hotpath.cuh"
 
+#ifndef CAVB_NVT_CTAS_PER_SM
+#define CAVB_NVT_CTAS_PER_SM 4 // grid cap of the element-wise harness kernels, in CTAs of 256 threads per SM: one wave (A/B at 1M: 8 -> 4: path C 55.7 -> 51.4 us, D 48.6 -> 44.7 us)
+#endif
+
 namespace cavb
     {
 // step one: alpha from the KE left in Scalars by the previous step two (or by cavb200_bussi_ke);
@@ -564,7 +568,7 @@ static int nvt_one(cavb200_handle* h, double* pos, double* vel, const double* fo
     if (bussi)
         fill_bussi_constants(b, bussi);
     unsigned long long want = ((unsigned long long)N + 255) / 256;
-    const unsigned long long cap = (unsigned long long)h->num_sms * 8;
+    const unsigned long long cap = (unsigned long long)h->num_sms * CAVB_NVT_CTAS_PER_SM;
     const int grid = (int)(want < cap ? want : cap);
     if (r1)
         k_nvt_one<true><<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)pos, (double4*)vel, (const double4*)force, N, dt,
@@ -588,7 +592,7 @@ static int nvt_two(cavb200_handle* h, double* vel, const double* force, uint32_t
     b.first = group_first;
     b.n = n_group;
     unsigned long long want = ((unsigned long long)N + 255) / 256;
-    unsigned long long cap = (unsigned long long)h->num_sms * 8;
+    unsigned long long cap = (unsigned long long)h->num_sms * CAVB_NVT_CTAS_PER_SM;
     if (cap > (unsigned long long)MAX_PARTIALS)
         cap = MAX_PARTIALS;
     const int grid = (int)(want < cap ? want : cap);
