@@ -31,6 +31,11 @@
  *     CUDA device cavb200_create fails.
  *   - a handle owns its workspace and is bound to one device; calls on one handle must be issued
  *     from one host thread at a time (HOOMD's integrator thread).
+ *   - the force / Bussi / step / md_step_fused / shard kernels are PERSISTENT: their grids fill the device and the CTAs
+ *     hand results to each other while resident.  Issue them so that no two of them (of this or of another handle) can
+ *     run at the same time on one device -- one stream, as HOOMD does, or streams ordered by events (what
+ *     cavb200_step_host_submit does internally).  If co-residency fails anyway the hand-off gives up after 50 ms: the
+ *     call's outputs are not written, the *_read calls return cudaErrorLaunchTimeout / err = 2; nothing hangs.
  */
 #ifndef CAVB200_H
 #define CAVB200_H
