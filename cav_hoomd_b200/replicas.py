@@ -28,3 +28,14 @@ def replicas_for_rank(replicas, rank: int, world_size: int):
 
 def gpu_for_replica(replicas, replica: int, n_gpus: int) -> int:
     return sorted(replicas).index(replica) % n_gpus
+
+
+def frames_for_rank(n_frames: int, rank: int, world_size: int, block: int = 16):
+    """F(k,t) over several GPUs: frames are independent, so rank r takes the blocks of `block`
+    consecutive frames b with b mod world_size == r -- no data-path collective; rho[t][k] of all frames is gathered
+    once at the end (2*T*K doubles) before the origin/lag table is formed.  -> list of (first, count)."""
+    out = []
+    for b, first in enumerate(range(0, n_frames, block)):
+        if b % world_size == rank:
+            out.append((first, min(block, n_frames - first)))
+    return out

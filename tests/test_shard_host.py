@@ -103,3 +103,64 @@ def test_shard_system_refuses_a_split_thermostat_group():
     s = synth.make_system(1000, photon="middle")
     with pytest.raises(ValueError):
         shard.shard_system(s, 0, 2)
+
+
+def _fkt_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from cav_hoomd_b200 import replicas, synth
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T, K, n = 23, 6, 400
+        s = synth.make_system(n)
+        rng = np.random.default_rng(3)
+        frames = s.pos[None, :, :3] + 0.1 * np.cumsum(rng.standard_normal((T, s.N, 3)), axis=0)
+        kvec = O.numpy_fibonacci_sphere(K) * 0.8
+        mine = replicas.frames_for_rank(T, rank, world, block=4)
+        rho = torch.zeros((T, K, 2), dtype=torch.float64)
+        for first, count in mine:                       # on a GPU box: one cavb200_rhok launch per block
+            for t in range(first, first + count):
+                r = O.numpy_density_field(frames[t], kvec)
+                rho[t, :, 0] = torch.from_numpy(r.real.copy())
+                rho[t, :, 1] = torch.from_numpy(r.imag.copy())
+        dist.all_reduce(rho)                            # the one exchange: 2*T*K doubles at the end
+        full = np.stack([O.numpy_density_field(frames[t], kvec) for t in range(T)])
+        got = rho[..., 0].numpy() + 1j * rho[..., 1].numpy()
+        covered = sorted(t for f, c in mine for t in range(f, f + c))
+        q.put((rank, bool(np.array_equal(got, full)), covered))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fkt_frames_partition_over_ranks_gloo():
+    """SURVEY.md 8e, F(k,t): frames are independent -> blocks of frames round-robin over ranks, no data-path collective,
+    one all-reduce of rho at the end.  Two gloo ranks on CPU (the NumPy restatement stands in for cavb200_rhok)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fkt_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert sorted(res[0][2] + res[1][2]) == list(range(23)) and not set(res[0][2]) & set(res[1][2])
+
+
+def test_frames_for_rank_covers_every_frame_once():
+    from cav_hoomd_b200 import replicas
+    for T in (0, 1, 15, 16, 17, 1000):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                for first, count in replicas.frames_for_rank(T, r, world):
+                    assert 0 < count <= 16
+                    seen.extend(range(first, first + count))
+            assert sorted(seen) == list(range(T))
