@@ -30,7 +30,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     N, K, T = args.n + 1, args.K, args.frames
-    h = capi.Handle(0)
+    # several GPUs (torchrun): frames are independent, every rank takes its blocks of T frames of the `origins` frames
+    # (cav_hoomd_b200.replicas.frames_for_rank), no data-path collective; time = max over ranks
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+    h = capi.Handle(local)
     if args.threads:
         h.set_tuning(rhok_threads=args.threads)
     s = synth.make_system(args.n)
@@ -53,6 +60,10 @@ def main():
         h.rhok(d_frames[k % nbuf], args.stride, N * args.stride, N, T, d_k, K, d_rho, st.ptr)
     capi.sync()
     launches = max(4, min(40, args.origins // T))
+    if world > 1:
+        from cav_hoomd_b200 import replicas
+        launches = len(replicas.frames_for_rank(args.origins, rank, world, block=T))
+        dist.barrier()
     e0, e1 = capi.Event(), capi.Event()
     l0 = h.launch_count
     e0.record(st.ptr)
@@ -60,6 +71,18 @@ def main():
         h.rhok(d_frames[k % nbuf], args.stride, N * args.stride, N, T, d_k, K, d_rho, st.ptr)
     e1.record(st.ptr)
     ms = e1.elapsed_ms_since(e0)
+    if world > 1:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_all = float(t.item())
+        if rank == 0:
+            print(json.dumps({"workload": f"F(k,t) over {world} GPUs: {args.origins} frames of N={N} particles, K={K}, blocks of {T} frames "
+                                          "round-robin over ranks, no collective in the data path",
+                              "n_gpus": world, "seconds_for_origins_field_sum": ms_all * 1e-3,
+                              "sincos_pairs_per_s": N * K * args.origins / (ms_all * 1e-3), "launches_per_rank": launches}))
+        dist.destroy_process_group()
+        return
     per_frame_ms = ms / (launches * T)
     pairs_per_s = N * K / (per_frame_ms * 1e-3)
     rho = d_rho.numpy(st.ptr)
