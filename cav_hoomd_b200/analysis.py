@@ -33,6 +33,19 @@ class DensityField:
     def compute_density_field(self, positions: np.ndarray) -> np.ndarray:
         """compute_density_field(snapshot, wavevectors) for host positions [N,3] or [T,N,3]
         (reference analysis.py:34-47) -> complex rho[K] or [T,K]."""
+        if np.asarray(positions).dtype == np.float32 and np.asarray(positions).shape[-1] == 3:
+            # GSD trajectories: float32 xyz goes to the device as it is (12 B/particle/frame) and is widened there
+            p = np.ascontiguousarray(positions, dtype=np.float32)
+            single = p.ndim == 2
+            if single:
+                p = p[None]
+            T, N, _ = p.shape
+            d_pos = capi.DeviceArray.from_numpy(p)
+            d_rho = capi.DeviceArray((T, self.K, 2), np.float64)
+            self._handle.rhok_f32(d_pos, 3 * N, N, T, self._d_k, self.K, d_rho)
+            r = d_rho.numpy()
+            rho = r[..., 0] + 1j * r[..., 1]
+            return rho[0] if single else rho
         p = np.ascontiguousarray(positions, dtype=np.float64)
         single = p.ndim == 2
         if single:

@@ -83,6 +83,7 @@ _SIGNATURES = {
     "cavb200_track_record": (C.c_int, [_vp, _u64, _vp, _u32, _vp]),
     "cavb200_track_read": (C.c_int, [_vp, _dp, _u32, C.POINTER(_u32), C.POINTER(_u64), _vp]),
     "cavb200_rhok": (C.c_int, [_vp, _vp, _u32, _u64, _u32, _u32, _vp, _u32, _vp, _vp]),
+    "cavb200_rhok_f32": (C.c_int, [_vp, _vp, _u64, _u32, _u32, _vp, _u32, _vp, _vp]),
     "cavb200_fkt": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp]),
     "cavb200_shard_nccl_unique_id": (C.c_int, [_vp]),
     "cavb200_shard_init_nccl": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
@@ -467,6 +468,10 @@ class Handle:
     def rhok(self, pos, stride, frame_stride, N, T, kvec, K, rho, stream=None):
         check(self.lib.cavb200_rhok(self.h, _ptr(pos), stride, frame_stride, N, T, _ptr(kvec), K, _ptr(rho), stream),
               "cavb200_rhok")
+
+    def rhok_f32(self, pos_xyz, frame_stride, N, T, kvec, K, rho, stream=None):
+        check(self.lib.cavb200_rhok_f32(self.h, _ptr(pos_xyz), frame_stride, N, T, _ptr(kvec), K, _ptr(rho), stream),
+              "cavb200_rhok_f32")
 
     def fkt(self, rho, T, K, n_origins, n_lags, out, stream=None):
         check(self.lib.cavb200_fkt(self.h, _ptr(rho), T, K, n_origins, n_lags, _ptr(out), stream), "cavb200_fkt")

@@ -19,6 +19,7 @@ namespace cavb
 #define RHOK_MIN_CTAS 2
 #endif
 constexpr int RHOK_TILE = 1024; // particles per shared-memory tile (24 KB)
+constexpr uint32_t RHOK_F32 = 13;  // internal `stride` code: float32 xyz positions (frame_stride then counts floats)
 
 // sin and cos of one argument, |x| < 2^20, both to < 1 ulp-ish (abs. error ~2e-16).
 // The library sincos() costs ~70 issue slots per call here, two thirds of them integer/selection/slow-path
@@ -130,6 +131,17 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
                 sx[j] = r.x;
                 sy[j] = r.y;
                 sz[j] = r.z;
+                }
+            }
+        else if (stride == RHOK_F32)
+            {
+            // float32 xyz, the way GSD stores positions: widened exactly, as NumPy does in np.dot(f32, f64)
+            const float* src = reinterpret_cast<const float*>(pos) + (unsigned long long)t * frame_stride + 3ull * base;
+            for (uint32_t e = tid; e < 3 * n; e += blockDim.x)
+                {
+                const double v = (double)__ldg(src + e);
+                const uint32_t j = e / 3, c = e - 3 * j;
+                (c == 0 ? sx : (c == 1 ? sy : sz))[j] = v;
                 }
             }
         else
@@ -267,16 +279,18 @@ __global__ void k_fkt(const double* __restrict__ rho, uint32_t T, uint32_t K, ui
 
 using namespace cavb;
 
-extern "C" int cavb200_rhok(cavb200_handle* h, const double* pos, uint32_t stride, uint64_t frame_stride, uint32_t N,
-                            uint32_t T, const double* kvec, uint32_t K, double* rho, void* stream)
+static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, uint64_t frame_stride, uint32_t N,
+                       uint32_t T, const double* kvec, uint32_t K, double* rho, void* stream)
     {
     if (!h)
         return (int)cudaErrorInvalidValue;
     if (T == 0 || K == 0)
         return 0;
-    if (!kvec || !rho || (N > 0 && !pos) || (stride != 3 && stride != 4))
+    if (!kvec || !rho || (N > 0 && !pos) || (stride != 3 && stride != 4 && stride != RHOK_F32))
         return (int)cudaErrorInvalidValue;
     if (stride == 4 && ((reinterpret_cast<uintptr_t>(pos) & 31) || (frame_stride & 3)))
+        return (int)cudaErrorMisalignedAddress;
+    if (stride == RHOK_F32 && (reinterpret_cast<uintptr_t>(pos) & 3))
         return (int)cudaErrorMisalignedAddress;
     cudaStream_t s = (cudaStream_t)stream;
     if (N == 0)
@@ -328,6 +342,20 @@ extern "C" int cavb200_rhok(cavb200_handle* h, const double* pos, uint32_t strid
         h->launches += 1;
         }
     return 0;
+    }
+
+extern "C" int cavb200_rhok(cavb200_handle* h, const double* pos, uint32_t stride, uint64_t frame_stride, uint32_t N,
+                            uint32_t T, const double* kvec, uint32_t K, double* rho, void* stream)
+    {
+    if (stride != 3 && stride != 4)
+        return (int)cudaErrorInvalidValue;
+    return rhok_launch(h, pos, stride, frame_stride, N, T, kvec, K, rho, stream);
+    }
+
+extern "C" int cavb200_rhok_f32(cavb200_handle* h, const float* pos_xyz, uint64_t frame_stride, uint32_t N, uint32_t T,
+                                const double* kvec, uint32_t K, double* rho, void* stream)
+    {
+    return rhok_launch(h, reinterpret_cast<const double*>(pos_xyz), RHOK_F32, frame_stride, N, T, kvec, K, rho, stream);
     }
 
 extern "C" int cavb200_fkt(cavb200_handle* h, const double* rho, uint32_t T, uint32_t K, uint32_t n_origins,

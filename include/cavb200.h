@@ -249,6 +249,12 @@ int cavb200_track_read(cavb200_handle* h, double* out, uint32_t max_records, uin
  * rho: double[2*K*T] (device), interleaved {re, im}.  Deterministic (fixed-order) reduction. */
 int cavb200_rhok(cavb200_handle* h, const double* pos, uint32_t stride, uint64_t frame_stride,
                  uint32_t N, uint32_t T, const double* kvec, uint32_t K, double* rho, void* stream);
+/* The same for float32 xyz positions, the way a GSD trajectory stores them (particles/position, Nx3 float32;
+ * reference examples/05_advanced_run.py:1231-1246 writes the trajectory the analysis reads): 12 B/particle/frame
+ * instead of 24-32 cross PCIe and HBM; the values are widened exactly, as NumPy does in np.dot(float32, float64)
+ * (analysis.py:42).  frame t starts at pos_xyz + t*frame_stride FLOATS. */
+int cavb200_rhok_f32(cavb200_handle* h, const float* pos_xyz, uint64_t frame_stride, uint32_t N, uint32_t T,
+                     const double* kvec, uint32_t K, double* rho, void* stream);
 /* F[o][l] = mean_k Re(rho[o][k] * conj(rho[o+l][k])) for origins o < n_origins, lags l < n_lags
  * with o + l < T (compute_field_autocorr, analysis.py:359-364).  out: double[n_origins*n_lags],
  * entries with o + l >= T are set to NaN. */

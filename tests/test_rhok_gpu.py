@@ -92,7 +92,8 @@ def test_fkt_from_a_gsd_trajectory(tmp_path, handle):
     gsdio.write_gsd(path, frames)
     with gsdio.open_gsd(path) as f:
         assert len(f) == 6 and [f[i].step for i in range(6)] == [0, 100, 200, 300, 400, 500]
-        pos = np.stack([f[i].position.astype(np.float64) for i in range(len(f))])
+        pos = np.stack([f[i].position for i in range(len(f))])   # float32, as stored: DensityField takes the f32 path
+        assert pos.dtype == np.float32
     kvec = analysis.generate_fibonacci_sphere(16) * 0.7
     field = analysis.DensityField(kvec, handle)
     rho = field.compute_density_field(pos)
@@ -103,3 +104,26 @@ def test_fkt_from_a_gsd_trajectory(tmp_path, handle):
     d_rho = capi.DeviceArray.from_numpy(np.stack([rho.real, rho.imag], axis=-1))
     F = field.autocorrelation(d_rho, 6, 2, 4)
     assert abs(F[0, 3] - f0) <= 1e-9 * abs(f0)
+
+
+@pytest.mark.parametrize("N,T,K", [(1, 1, 1), (1000, 3, 7), (5001, 2, 64), (150000, 4, 33)])
+def test_rhok_float32_positions(handle, N, T, K):
+    """cavb200_rhok_f32 (GSD-style float32 xyz): bit-identical to cavb200_rhok on the same values widened on the host
+    (the kernel widens exactly), and within 1e-9*N of the NumPy restatement np.dot(float32 positions, float64 k)."""
+    rng = np.random.default_rng(N + T)
+    pos32 = (rng.uniform(-40, 40, size=(T, N, 3))).astype(np.float32)
+    kvec = O.numpy_fibonacci_sphere(max(K, 2))[:K] * 0.9
+    d_k = capi.DeviceArray.from_numpy(kvec)
+    d32 = capi.DeviceArray.from_numpy(pos32)
+    d64 = capi.DeviceArray.from_numpy(pos32.astype(np.float64))
+    r32 = capi.DeviceArray((T, K, 2), np.float64)
+    r64 = capi.DeviceArray((T, K, 2), np.float64)
+    handle.rhok_f32(d32, 3 * N, N, T, d_k, K, r32)
+    handle.rhok(d64, 3, 3 * N, N, T, d_k, K, r64)
+    a, b = r32.numpy(), r64.numpy()
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    for t in range(T):
+        ref = O.numpy_density_field(pos32[t], kvec)
+        assert np.abs((a[t, :, 0] + 1j * a[t, :, 1]) - ref).max() <= 1e-9 * N
+    with pytest.raises(capi.CavbError):
+        handle.rhok(d64, 13, 3 * N, N, T, d_k, K, r64)  # the internal float32 code is not a public stride

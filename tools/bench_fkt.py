@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16, help="frames per launch")
     ap.add_argument("--origins", type=int, default=1000)
     ap.add_argument("--stride", type=int, default=4, choices=[3, 4])
+    ap.add_argument("--f32", action="store_true", help="float32 xyz frames (GSD layout) through cavb200_rhok_f32")
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -53,7 +54,13 @@ def main():
         if args.stride == 4:
             frames[t, :, 3] = cur[:, 3]
     nbuf = max(2, int(400e6 // frames.nbytes) + 1)
-    d_frames = [capi.DeviceArray.from_numpy(frames) for _ in range(nbuf)]
+    if args.f32:
+        frames32 = np.ascontiguousarray(frames[:, :, :3], dtype=np.float32)
+        d_frames = [capi.DeviceArray.from_numpy(frames32) for _ in range(nbuf)]
+        _rhok = h.rhok
+        h.rhok = lambda d, stride, fs, N_, T_, dk, K_, drho, stream=None: h.rhok_f32(d, 3 * N_, N_, T_, dk, K_, drho, stream)
+    else:
+        d_frames = [capi.DeviceArray.from_numpy(frames) for _ in range(nbuf)]
     d_rho = capi.DeviceArray((T, K, 2), np.float64)
     st = capi.Stream()
     for k in range(3):
@@ -102,7 +109,8 @@ def main():
         "workload": f"F(k,t): N={N} particles, K={K} wave vectors, {T} frames per launch, stride {args.stride} doubles/particle",
         "ms_per_frame": per_frame_ms, "sincos_pairs_per_s": pairs_per_s,
         "seconds_for_origins": per_frame_ms * 1e-3 * args.origins + ms_corr * 1e-3, "origins": args.origins,
-        "position_GBs": N * 8 * args.stride / (per_frame_ms * 1e-3) / 1e9,
+        "position_GBs": N * (12 if args.f32 else 8 * args.stride) / (per_frame_ms * 1e-3) / 1e9,
+        "positions": "float32 xyz (cavb200_rhok_f32)" if args.f32 else f"float64, stride {args.stride}",
         "ms_correlation_all_origins_x_lags": ms_corr, "gpu_launches": h.launch_count - l0,
     }
     if not args.no_cpu:
@@ -113,7 +121,7 @@ def main():
         dt = time.perf_counter() - t0
         d_one = capi.DeviceArray.from_numpy(np.ascontiguousarray(frames[0, :n_s, :3]))
         d_r1 = capi.DeviceArray((1, K, 2), np.float64)
-        h.rhok(d_one, 3, n_s * 3, n_s, 1, d_k, K, d_r1, st.ptr)
+        (_rhok if args.f32 else h.rhok)(d_one, 3, n_s * 3, n_s, 1, d_k, K, d_r1, st.ptr)
         got = d_r1.numpy(st.ptr)[0]
         err = np.abs((got[:, 0] + 1j * got[:, 1]) - ref).max() / np.abs(ref).max()
         out["cpu_numpy"] = {"sincos_pairs_per_s": n_s * K / dt, "sample": f"{n_s} particles x {K} k, 1 frame, 1 thread",
