@@ -1,24 +1,42 @@
-// BussiReservoirThermostat.cc -- pybind11 export, same names as the reference
-// (reference src/BussiReservoirThermostat.cc:9-30) plus the opt-in fused_rescale property.
+// BussiReservoirThermostat.cc -- pybind11 registration of the B200 thermostat host class.
+// The Python wrapper (reference src/bussi_reservoir/thermostats.py) looks these names up, so the class name,
+// constructor signature, the two read/write properties and the seven methods are those of the reference's
+// export (src/BussiReservoirThermostat.cc:9-30); `fused_rescale` is the one addition.
 #include "BussiReservoirThermostat.h"
 
 namespace hoomd::md
     {
+namespace
+    {
+using Self = BussiReservoirThermostat;
+
+// the six reservoir read-outs share one signature: register them from a table
+struct Getter
+    {
+    const char* name;
+    Scalar (Self::*fn)();
+    };
+const Getter reservoir_getters[] = {
+    {"getReservoirEnergyTranslational", &Self::getReservoirEnergyTranslational},
+    {"getReservoirEnergyRotational", &Self::getReservoirEnergyRotational},
+    {"getTotalReservoirEnergy", &Self::getTotalReservoirEnergy},
+    {"getInstantaneousReservoirTranslational", &Self::getInstantaneousReservoirTranslational},
+    {"getInstantaneousReservoirRotational", &Self::getInstantaneousReservoirRotational},
+    {"getInstantaneousReservoirTotal", &Self::getInstantaneousReservoirTotal},
+};
+    } // namespace
+
 void export_BussiReservoirThermostat(pybind11::module& m)
     {
-    pybind11::class_<BussiReservoirThermostat, Thermostat, std::shared_ptr<BussiReservoirThermostat>>(
-        m, "BussiReservoirThermostat")
-        .def(pybind11::init<std::shared_ptr<Variant>, std::shared_ptr<ParticleGroup>, std::shared_ptr<ComputeThermo>,
-                            std::shared_ptr<SystemDefinition>, Scalar>())
-        .def_property("tau", &BussiReservoirThermostat::getTau, &BussiReservoirThermostat::setTau)
-        .def_property("kT", &BussiReservoirThermostat::getT, &BussiReservoirThermostat::setT)
-        .def_property("fused_rescale", &BussiReservoirThermostat::getFusedRescale, &BussiReservoirThermostat::setFusedRescale)
-        .def("getReservoirEnergyTranslational", &BussiReservoirThermostat::getReservoirEnergyTranslational)
-        .def("getReservoirEnergyRotational", &BussiReservoirThermostat::getReservoirEnergyRotational)
-        .def("getTotalReservoirEnergy", &BussiReservoirThermostat::getTotalReservoirEnergy)
-        .def("getInstantaneousReservoirTranslational", &BussiReservoirThermostat::getInstantaneousReservoirTranslational)
-        .def("getInstantaneousReservoirRotational", &BussiReservoirThermostat::getInstantaneousReservoirRotational)
-        .def("getInstantaneousReservoirTotal", &BussiReservoirThermostat::getInstantaneousReservoirTotal)
-        .def("resetReservoirEnergy", &BussiReservoirThermostat::resetReservoirEnergy);
+    namespace py = pybind11;
+    py::class_<Self, Thermostat, std::shared_ptr<Self>> cls(m, "BussiReservoirThermostat");
+    cls.def(py::init<std::shared_ptr<Variant>, std::shared_ptr<ParticleGroup>, std::shared_ptr<ComputeThermo>,
+                     std::shared_ptr<SystemDefinition>, Scalar>());
+    cls.def_property("kT", &Self::getT, &Self::setT);
+    cls.def_property("tau", &Self::getTau, &Self::setTau);
+    cls.def_property("fused_rescale", &Self::getFusedRescale, &Self::setFusedRescale);
+    for (const Getter& g : reservoir_getters)
+        cls.def(g.name, g.fn);
+    cls.def("resetReservoirEnergy", &Self::resetReservoirEnergy);
     }
     } // namespace hoomd::md
