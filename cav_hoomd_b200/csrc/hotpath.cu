@@ -5,6 +5,9 @@
 #ifndef CAVB_FOLDER_WARMUP
 #define CAVB_FOLDER_WARMUP 1
 #endif
+#ifndef CAVB_FUSED_VEL_PREFETCH
+#define CAVB_FUSED_VEL_PREFETCH 4 // velocities per thread fetched before the hand-off of the Bussi-only call
+#endif
 #ifndef CAVB_VEL_PREFETCH
 #define CAVB_VEL_PREFETCH 4 // velocities per thread fetched before the wait for alpha (k_split_folder)
 #endif
@@ -86,6 +89,15 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     if (my_stamps)
         my_stamps[1] = globaltimer_ns();
     const unsigned long long epoch = sc.epoch;
+    // Bussi-only call: the whole grid now waits ~3.5 us for alpha with nothing to do; fetch the first velocities of
+    // the rescale pass (L2 hits) before the wait, so that the pass starts with stores (as in k_split_folder)
+    constexpr bool PRE = !FORCE && BUSSI;
+    // (only while the velocities still sit in L2 after the KE pass: 262k 7.24 -> 6.30 us, 1M 16.66 -> 16.03 us, but
+    // 4M 63.1 -> 64.3 us, where the early loads go to HBM)
+    const bool pre = PRE && b.rescale && b.gidx == nullptr && b.first == 0 && b.n <= 2000000u;
+    VelPrefetch<PRE ? CAVB_FUSED_VEL_PREFETCH : 1> pv;
+    if (pre)
+        pv = prefetch_vel<PRE ? CAVB_FUSED_VEL_PREFETCH : 1>(b, whole_grid());
     combine_phase<FORCE, BUSSI, true, true>(recs, (int)gridDim.x, epoch, f, b, sc, scalars, blockIdx.x == 0, my_stamps);
     if (my_stamps)
         my_stamps[3] = globaltimer_ns();
@@ -95,7 +107,13 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         return;
     // from here on the next kernel's CTAs may take the SMs this grid's CTAs leave
     pdl_launch_dependents();
-    apply_phase<FORCE, BUSSI, UNROLL>(sc.fin, f, b);
+    if (pre)
+        {
+        if (sc.fin.bussi_ok && sc.fin.alpha != 1.0) // as apply_phase
+            rescale_prefetched<PRE ? CAVB_FUSED_VEL_PREFETCH : 1, UNROLL>(sc.fin.alpha, b, whole_grid(), pv);
+        }
+    else
+        apply_phase<FORCE, BUSSI, UNROLL>(sc.fin, f, b);
     if (my_stamps)
         my_stamps[4] = globaltimer_ns();
     }
