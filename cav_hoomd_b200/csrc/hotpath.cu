@@ -5,6 +5,9 @@
 #ifndef CAVB_FOLDER_WARMUP
 #define CAVB_FOLDER_WARMUP 1
 #endif
+#ifndef CAVB_FUSED_CHARGE_PREFETCH
+#define CAVB_FUSED_CHARGE_PREFETCH 4 // charges per thread fetched before the hand-off of the force-only call
+#endif
 #ifndef CAVB_FUSED_VEL_PREFETCH
 #define CAVB_FUSED_VEL_PREFETCH 4 // velocities per thread fetched before the hand-off of the Bussi-only call
 #endif
@@ -98,6 +101,10 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     VelPrefetch<PRE ? CAVB_FUSED_VEL_PREFETCH : 1> pv;
     if (pre)
         pv = prefetch_vel<PRE ? CAVB_FUSED_VEL_PREFETCH : 1>(b, whole_grid());
+    constexpr bool PREF = FORCE && !BUSSI;
+    ChargePrefetch<PREF ? CAVB_FUSED_CHARGE_PREFETCH : 1> cpre;
+    if (PREF)
+        cpre = prefetch_charge<PREF ? CAVB_FUSED_CHARGE_PREFETCH : 1>(f, whole_grid());
     combine_phase<FORCE, BUSSI, true, true>(recs, (int)gridDim.x, epoch, f, b, sc, scalars, blockIdx.x == 0, my_stamps);
     if (my_stamps)
         my_stamps[3] = globaltimer_ns();
@@ -107,7 +114,9 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         return;
     // from here on the next kernel's CTAs may take the SMs this grid's CTAs leave
     pdl_launch_dependents();
-    if (pre)
+    if (PREF)
+        forces_prefetched<PREF ? CAVB_FUSED_CHARGE_PREFETCH : 1, UNROLL>(sc.fin, f, whole_grid(), cpre);
+    else if (pre)
         {
         if (sc.fin.bussi_ok && sc.fin.alpha != 1.0) // as apply_phase
             rescale_prefetched<PRE ? CAVB_FUSED_VEL_PREFETCH : 1, UNROLL>(sc.fin.alpha, b, whole_grid(), pv);

@@ -1079,8 +1079,49 @@ __device__ __forceinline__ void rescale_prefetched(double alpha, const BussiIn& 
         }
     }
 
-// (The same trick for the force pass -- the first charges fetched under the KE merge tree -- measured slightly
-// worse, 31.37 vs 31.25 us, and is not used.)
+// The same for the force pass of the force-only call (k_fused<1,0>): the first PRE charges of every thread are
+// fetched before the hand-off.  (In k_split_folder, where they would be fetched under the KE merge tree, it measured
+// slightly worse, 31.37 vs 31.25 us, and is not used there.)
+template<int PRE> struct ChargePrefetch
+    {
+    double c[PRE];
+    };
+template<int PRE> __device__ __forceinline__ ChargePrefetch<PRE> prefetch_charge(const ForceIn& f, const StreamGrid g)
+    {
+    ChargePrefetch<PRE> p;
+    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
+    const unsigned long long i0 = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < PRE; k++)
+        p.c[k] = (i0 + k * stride < (unsigned long long)f.N) ? __ldg(f.charge + i0 + k * stride) : 0.0;
+    return p;
+    }
+template<int PRE, int U>
+__device__ __forceinline__ void forces_prefetched(const Final& fin, const ForceIn& f, const StreamGrid g,
+                                                  const ChargePrefetch<PRE>& p)
+    {
+    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
+    const unsigned long long N = f.N;
+    unsigned long long i = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < PRE; k++)
+        if (i + k * stride < N)
+            st256_stream(f.force + i + k * stride, force_of(i + k * stride, p.c[k], fin, f));
+    i += (unsigned long long)PRE * stride;
+    for (; i + (U - 1) * stride < N; i += U * stride)
+        {
+        double c[U];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            c[k] = __ldg(f.charge + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            st256_stream(f.force + i + k * stride, force_of(i + k * stride, c[k], fin, f));
+        }
+    for (; i < N; i += stride)
+        st256_stream(f.force + i, force_of(i, __ldg(f.charge + i), fin, f));
+    }
+
 
 // ---- Final record hand-off (k_split_folder) -----------------------------------------------------
 // The folder CTA publishes what finalize() formed in the sector format of the reduce records
