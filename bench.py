@@ -269,9 +269,15 @@ def cpu_reference_throughput(n_mol: int, steps: int, cores: int):
     wall = time.perf_counter() - t0
     # every worker times only its own compute loop; the job rate is the sum of per-replica rates
     rate = sum(n / dt for n, dt in res) / 1e6
+    # one replica alone on the machine (SURVEY.md 8d asks for both): the per-core rate without the others
+    # competing for memory bandwidth
+    with ctx.Pool(1) as pool:
+        n1, dt1 = pool.map(_cpu_worker, [(n_mol, 0, max(3, steps // 3), kind)])[0]
     return dict(value=rate, unit=UNIT, cores=cores, kind=kind,
                 sample=f"{cores} concurrent 1-thread replicas x {steps} steps of the {n_mol + 1}-particle box "
-                       f"(cavity force + Bussi), wall {wall:.1f} s incl. setup")
+                       f"(cavity force + Bussi), wall {wall:.1f} s incl. setup",
+                single_process={"value": n1 / dt1 / 1e6, "unit": UNIT, "cores": 1,
+                                "sample": f"1 replica x {max(3, steps // 3)} steps, alone on the host"})
 
 
 def run_reference(args):
