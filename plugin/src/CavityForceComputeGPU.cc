@@ -3,6 +3,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace hoomd
     {
@@ -118,6 +119,42 @@ pybind11::tuple CavityForceComputeGPU::getDipole()
     return pybind11::make_tuple(m_dipole[0], m_dipole[1], m_dipole[2]);
     }
 
+void CavityForceComputeGPU::trackOpen(unsigned int capacity)
+    {
+    check(cavb200_track_open(m_handle, capacity), "cavb200_track_open");
+    }
+
+void CavityForceComputeGPU::trackSetReference()
+    {
+    check(cavb200_track_set_reference(m_handle, nullptr), "cavb200_track_set_reference");
+    }
+
+void CavityForceComputeGPU::trackRecord(uint64_t timestep)
+    {
+    // asynchronous, ordered after this step's force kernel on HOOMD's stream; the photon's kinetic energy needs
+    // the velocities, everything else is already on the device
+    ArrayHandle<Scalar4> d_vel(m_pdata->getVelocities(), access_location::device, access_mode::read);
+    check(cavb200_track_record(m_handle, timestep, reinterpret_cast<const double*>(d_vel.data), m_pdata->getN(), nullptr),
+          "cavb200_track_record");
+    }
+
+pybind11::list CavityForceComputeGPU::trackRead(unsigned int max_records)
+    {
+    std::vector<double> buf((size_t)max_records * CAVB200_TRACK_WORDS + 1);
+    uint32_t n = 0;
+    uint64_t total = 0;
+    check(cavb200_track_read(m_handle, buf.data(), max_records, &n, &total, nullptr), "cavb200_track_read");
+    pybind11::list out;
+    for (uint32_t r = 0; r < n; r++)
+        {
+        pybind11::tuple row(CAVB200_TRACK_WORDS);
+        for (int k = 0; k < CAVB200_TRACK_WORDS; k++)
+            row[k] = buf[(size_t)r * CAVB200_TRACK_WORDS + k];
+        out.append(row);
+        }
+    return out;
+    }
+
 namespace detail
     {
 void export_CavityForceComputeGPU(pybind11::module& m)
@@ -133,7 +170,11 @@ void export_CavityForceComputeGPU(pybind11::module& m)
         .def("getHarmonicEnergy", &CavityForceComputeGPU::getHarmonicEnergy)
         .def("getCouplingEnergy", &CavityForceComputeGPU::getCouplingEnergy)
         .def("getDipoleSelfEnergy", &CavityForceComputeGPU::getDipoleSelfEnergy)
-        .def("getDipole", &CavityForceComputeGPU::getDipole);
+        .def("getDipole", &CavityForceComputeGPU::getDipole)
+        .def("trackOpen", &CavityForceComputeGPU::trackOpen, pybind11::arg("capacity"))
+        .def("trackSetReference", &CavityForceComputeGPU::trackSetReference)
+        .def("trackRecord", &CavityForceComputeGPU::trackRecord, pybind11::arg("timestep"))
+        .def("trackRead", &CavityForceComputeGPU::trackRead, pybind11::arg("max_records"));
     }
     } // namespace detail
     } // namespace cavitymd

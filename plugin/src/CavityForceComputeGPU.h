@@ -39,6 +39,15 @@ class PYBIND11_EXPORT CavityForceComputeGPU : public ForceCompute
     //! total molecular dipole of the last step (not in the reference API; free with the reduction)
     pybind11::tuple getDipole();
 
+    //! Device-side trackers: what DipoleAutocorrelation / CavityModeTracker / EnergyTracker of the
+    //! reference get from a full cpu_local_snapshot every step (src/cavitymd/analysis.py:188,234,535,578,1327) is
+    //! appended on the device, one 128-byte record per call, and read back once per output period.
+    void trackOpen(unsigned int capacity);
+    void trackSetReference();
+    void trackRecord(uint64_t timestep);
+    //! newest min(max_records, stored) records, oldest first: list of 16-tuples (layout: include/cavb200.h)
+    pybind11::list trackRead(unsigned int max_records);
+
     protected:
     virtual void computeForces(uint64_t timestep);
 

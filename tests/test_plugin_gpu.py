@@ -116,3 +116,32 @@ def test_bussi_thermostat_zero_momenta_throws(mods):
     bus._inject_draws([0.1, 140.0])
     with pytest.raises(RuntimeError, match="non-zero initial momenta"):
         th.getRescalingFactorsOne(0, 0.005)
+
+
+def test_cavity_force_class_device_side_tracker(mods):
+    """trackOpen / trackSetReference / trackRecord / trackRead on the plugin class: the dipole autocorrelation and the
+    cavity-mode kinetic energy without a snapshot (reference src/cavitymd/analysis.py:18-31,222-224,1352-1354)."""
+    from oracle import oracle as O
+    shim, cav, _ = mods
+    s = synth.make_system(5000, replica=6)
+    sysdef, pd = make_sysdef(shim, s)
+    fc = cav.CavityForceComputeGPU(sysdef, 0.01, 1e-3)
+    fc.trackOpen(16)
+    fc.compute(0)
+    fc.trackSetReference()
+    d0 = O.numpy_total_dipole(s.pos[:, :3], s.image, s.charge, s.box)
+    pos = s.pos.copy()
+    for t in range(1, 4):
+        pos[:, :3] += 0.01 * t
+        pd.setPositions(pos)
+        fc.compute(t)
+        fc.trackRecord(t)
+    rows = fc.trackRead(8)
+    assert [int(r[0]) for r in rows] == [1, 2, 3] and all(len(r) == 16 for r in rows)
+    d3 = O.numpy_total_dipole(pos[:, :3], s.image, s.charge, s.box)
+    scale = np.abs(s.charge[:, None] * O.numpy_unwrap(pos[:, :3], s.image, s.box)).sum(axis=0)
+    assert np.all(np.abs(np.array(rows[-1][1:4]) - d3) <= 1e-10 * scale)
+    assert abs(rows[-1][10] - np.dot(d0, d3)) <= 1e-10 * np.dot(np.abs(d0), scale)
+    ke_ph = 0.5 * s.vel[-1, 3] * np.sum(s.vel[-1, :3] ** 2)
+    assert abs(rows[-1][11] - ke_ph) <= 1e-12 * ke_ph and int(rows[-1][15]) == s.N - 1
+    assert rows[-1][7] == fc.getHarmonicEnergy()
