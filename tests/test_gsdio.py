@@ -139,3 +139,50 @@ def test_triclinic_box_is_refused():
     fr.box = np.float32([5, 5, 5, 0.1, 0, 0])
     with pytest.raises(ValueError):
         gsdio.frame_to_system(fr)
+
+
+def test_round_trip_property(tmp_path):
+    """Property test (hypothesis): any frames of the supported chunks survive write -> read bit for bit, in both
+    name-list layouts; frame count, order and per-frame particle counts included."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @st.composite
+    def frames(draw):
+        nfr = draw(st.integers(1, 4))
+        out = []
+        for k in range(nfr):
+            N = draw(st.integers(0, 40))
+            ntypes = draw(st.integers(1, 4))
+            types = [draw(st.text(alphabet="ABCLNOXYZ", min_size=1, max_size=5)) for _ in range(ntypes)]
+            seed = draw(st.integers(0, 2 ** 31 - 1))
+            r = np.random.default_rng(seed)
+            fr = gsdio.Frame(step=draw(st.integers(0, 2 ** 40)), N=N, types=types)
+            fr.box = np.float32([r.uniform(1, 50), r.uniform(1, 50), r.uniform(1, 50), 0, 0, 0])
+            fr.typeid = r.integers(0, ntypes, size=N).astype(np.uint32)
+            fr.mass = r.uniform(0.5, 3e4, size=N).astype(np.float32)
+            fr.charge = r.normal(size=N).astype(np.float32)
+            fr.diameter = np.ones(N, np.float32)
+            fr.position = r.normal(scale=20, size=(N, 3)).astype(np.float32)
+            fr.velocity = r.normal(scale=1e-3, size=(N, 3)).astype(np.float32)
+            fr.image = r.integers(-3, 4, size=(N, 3)).astype(np.int32)
+            out.append(fr)
+        return out
+
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(frames(), st.sampled_from([(1, 0), (2, 0)]))
+    def check(frs, layer):
+        counter[0] += 1
+        path = str(tmp_path / f"p{counter[0]}.gsd")
+        gsdio.write_gsd(path, frs, file_layer=layer)
+        with gsdio.open_gsd(path) as f:
+            assert len(f) == len(frs)
+            for k, want in enumerate(frs):
+                got = f[k]
+                assert (got.step, got.N, got.types) == (want.step, want.N, want.types)
+                for name in ("typeid", "mass", "charge", "diameter", "position", "velocity", "image", "box"):
+                    a, b = getattr(got, name), getattr(want, name)
+                    assert a.dtype == b.dtype and np.array_equal(a.view(np.uint8), b.view(np.uint8)), name
+
+    check()
