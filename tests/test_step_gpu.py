@@ -223,3 +223,32 @@ def test_two_persistent_kernels_on_two_streams_never_hang(coracle):
         capi.sync()
         for h in hs:
             h.close()
+
+
+def test_step_randomised_cases(coracle):
+    """40 seeded random cases through the default tuning (fresh handle): sizes from 1 to 400k (both sides of the
+    full-grid boundary where the folder kernel takes over), photon placement, thermostat window, charge pattern,
+    coupling and draws all random; each against the oracle."""
+    h = capi.Handle(0)
+    rng = np.random.default_rng(20261018)
+    try:
+        for case in range(40):
+            n_mol = int(rng.choice([rng.integers(1, 400), rng.integers(400, 20000), rng.integers(20000, 400000)]))
+            photon = str(rng.choice(["last", "first", "middle", "absent", "duplicated"]))
+            charges = str(rng.choice(["neutral", "nonneutral", "zero"]))
+            s = synth.make_system(n_mol, replica=case, photon=photon, charges=charges)
+            if rng.random() < 0.5:
+                first, n = 0, (n_mol if photon in ("last", "absent") else s.N)
+            else:
+                first = int(rng.integers(0, s.N))
+                n = int(rng.integers(0, s.N - first + 1))
+            g = float(10.0 ** rng.uniform(-4, -2))
+            omegac = float(rng.uniform(0.005, 0.02))
+            dof = max(3.0 * n - 3.0, 0.0)
+            a = capi.BussiArgs(KT, float(rng.choice([TAU, 100.0, 0.0])), DT, dof, float(rng.normal()),
+                               float(rng.gamma(max(dof - 1.0, 2.0) / 2.0)))
+            out = run_step(h, s, first, n, a, omegac=omegac, g=g)
+            check_against_oracle(coracle, s, first, n, a, out, omegac=omegac, g=g)
+            assert out[5]["err"] == 0.0 or n == 0, (case, n_mol, photon, first, n)
+    finally:
+        h.close()
