@@ -136,8 +136,6 @@ int cavb200_create(cavb200_handle** out, int device)
     h->tune.unroll = 2;
     h->tune.pdl = 1;
     h->tune.auto_threads = 1;
-    h->tune.rhok_threads = 256;
-    h->tune.rhok_kblock = 8;
     h->shard.mode = 0;
     h->shard.nranks = 1;
     *out = h;
@@ -179,8 +177,6 @@ static int* tuning_slot(cavb::Tuning* t, const char* key)
     if (!strcmp(key, "unroll")) return &t->unroll;
     if (!strcmp(key, "stamps")) return &t->stamps;
     if (!strcmp(key, "pdl")) return &t->pdl;
-    if (!strcmp(key, "rhok_threads")) return &t->rhok_threads;
-    if (!strcmp(key, "rhok_kblock")) return &t->rhok_kblock;
     if (!strcmp(key, "ke_first")) return &t->ke_first;
     if (!strcmp(key, "auto_threads")) return &t->auto_threads;
     if (!strcmp(key, "md_shape")) return &t->md_shape;

@@ -80,8 +80,6 @@ struct Tuning
     int unroll;          // independent particle loads in flight per thread (1, 2 or 4)
     int pdl;             // launch with programmatic stream serialization (hides the launch gap)
     int stamps;          // debug: record per-CTA phase timestamps of the cooperative kernel
-    int rhok_threads;
-    int rhok_kblock;     // k-vectors handled per thread in the F(k,t) kernel
     int md_shape;        // cavb200_md_step_fused launch shape: 0 = one 768-thread CTA per SM (default), 1 = two 384-thread CTAs
     int auto_threads;    // step kernel: pick 320 / 352 / 384 threads per CTA from the particle count (1) or use `threads` (0)
     int ke_first;        // folder step kernel: thermostat half first (1) or dipole half first (0)

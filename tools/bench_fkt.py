@@ -27,7 +27,6 @@ def main():
     ap.add_argument("--origins", type=int, default=1000)
     ap.add_argument("--stride", type=int, default=4, choices=[3, 4])
     ap.add_argument("--f32", action="store_true", help="float32 xyz frames (GSD layout) through cavb200_rhok_f32")
-    ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     N, K, T = args.n + 1, args.K, args.frames
@@ -39,8 +38,6 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("gloo")
     h = capi.Handle(local)
-    if args.threads:
-        h.set_tuning(rhok_threads=args.threads)
     s = synth.make_system(args.n)
     rng = np.random.default_rng(7)
     kvec = synth.fibonacci_sphere(K) * 1.0
