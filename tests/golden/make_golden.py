@@ -3,8 +3,8 @@
 
 Run in the build container (needs /root/reference): the outputs come from oracle/_ref/libcavref.so,
 i.e. the reference's own src/CavityForceCompute.cc and src/BussiReservoirThermostat.h compiled
-verbatim by path (oracle/Makefile, oracle/ref_driver.cc), and for F(k,t) from the NumPy
-restatement of reference src/cavitymd/analysis.py:34-66,359-364 (oracle/oracle.py).
+verbatim by path (oracle/Makefile, oracle/ref_driver.cc), and for F(k,t) from the reference's own
+Python, src/cavitymd/analysis.py:34-66,359-364, imported by path under a stub `hoomd` (oracle/refpy.py).
 The reference's own tests hold no golden vectors for this path, so these are
 the pin.  Inputs are stored next to the outputs (small cases) so the fixtures do not depend on
 NumPy's random streams.
@@ -20,6 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from cav_hoomd_b200 import synth  # noqa: E402
 from oracle import oracle as O  # noqa: E402
+from oracle import refpy  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -77,19 +78,21 @@ def main():
         ref.bussi_close(h)
     np.savez_compressed(os.path.join(HERE, "bussi.npz"), **bout)
 
-    # F(k,t): NumPy restatement of the reference's Python
+    # F(k,t): the reference's own functions (compute_density_field, generate_fibonacci_sphere,
+    # FieldAutocorrelationTracker.compute_field_autocorr), executed from /root/reference
+    A = refpy.load().analysis
+    fa = A.FieldAutocorrelationTracker.compute_field_autocorr
     fout = {}
     s = synth.make_system(400, replica=3)
     frames = synth.random_walk_frames(s, 6, sigma=0.3)
-    kvec = O.numpy_fibonacci_sphere(50) * 1.0
-    rho = np.array([O.numpy_density_field(frames[t], kvec) for t in range(6)])
-    F = np.array([[O.numpy_field_autocorr(rho[o], rho[o + l]) if o + l < 6 else np.nan for l in range(4)]
-                  for o in range(6)])
+    kvec = A.generate_fibonacci_sphere(50) * 1.0
+    rho = np.array([A.compute_density_field(refpy.Snapshot(frames[t]), kvec) for t in range(6)])
+    F = np.array([[fa(None, rho[o], rho[o + l]) if o + l < 6 else np.nan for l in range(4)] for o in range(6)])
     fout["frames"] = frames
     fout["kvec"] = kvec
     fout["rho"] = rho
     fout["F"] = F
-    fout["fib64"] = O.numpy_fibonacci_sphere(64)
+    fout["fib64"] = A.generate_fibonacci_sphere(64)
     np.savez_compressed(os.path.join(HERE, "fkt.npz"), **fout)
     print("wrote cavity_force.npz, bussi.npz, fkt.npz")
 
