@@ -55,6 +55,7 @@ _SIGNATURES = {
     "cavb200_destroy": (C.c_int, [_vp]),
     "cavb200_error_string": (C.c_char_p, [C.c_int]),
     "cavb200_launch_count": (_u64, [_vp]),
+    "cavb200_fault_count": (_u64, [_vp]),
     "cavb200_debug_stamps": (C.c_int, [_vp, C.POINTER(C.c_uint64), _u32]),
     "cavb200_set_tuning": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "cavb200_get_tuning": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int)]),
@@ -328,6 +329,10 @@ class Handle:
     @property
     def launch_count(self) -> int:
         return int(self.lib.cavb200_launch_count(self.h))
+
+    @property
+    def fault_count(self) -> int:
+        return int(self.lib.cavb200_fault_count(self.h))
 
     # -- cavity force ------------------------------------------------------------------------
     def force(self, pos, charge, image, force, N, box, L_typeid, params: Params, stream=None):

@@ -38,6 +38,22 @@ void fill_bussi_constants(BussiIn& b, const cavb200_bussi_args* a)
     }
     } // namespace cavb
 
+namespace cavb
+    {
+int check_fault(cavb200_handle* h)
+    {
+    if (!h->fault_host || *(volatile unsigned long long*)h->fault_host == 0ull)
+        return 0;
+    // A persistent kernel of this handle gave up waiting for a CTA of its own grid: the grid was not co-resident,
+    // i.e. something else (another stream, another process under MPS) held SM slots.  The outputs of that call were not
+    // written.  From now on launch cooperatively -- the driver then guarantees co-residency -- and say so once.
+    *(volatile unsigned long long*)h->fault_host = 0ull;
+    h->tune.pdl = 0;
+    h->faults += 1;
+    return (int)cudaErrorLaunchTimeout;
+    }
+    } // namespace cavb
+
 namespace
     {
 inline bool misaligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
@@ -130,6 +146,22 @@ int cavb200_create(cavb200_handle** out, int device)
         cavb200_destroy(h);
         return (int)e;
         }
+    // the fault word: pinned host memory the kernels can store to (Scalars::fault), read by check_fault without a sync
+    if ((e = cudaHostAlloc((void**)&h->fault_host, 64, cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess)
+        {
+        cavb200_destroy(h);
+        return (int)e;
+        }
+    *h->fault_host = 0ull;
+        {
+        unsigned long long* dptr = nullptr;
+        if ((e = cudaHostGetDevicePointer((void**)&dptr, h->fault_host, 0)) != cudaSuccess
+            || (e = cudaMemcpy(&h->scalars->fault, &dptr, sizeof(dptr), cudaMemcpyHostToDevice)) != cudaSuccess)
+            {
+            cavb200_destroy(h);
+            return (int)e;
+            }
+        }
     h->tune.variant = 3; // split-phase step kernel with a folder CTA; force-only / Bussi-only calls use the fused kernel (variant 1)
     h->tune.threads = 384;
     h->tune.ctas_per_sm = 2;
@@ -155,11 +187,14 @@ int cavb200_destroy(cavb200_handle* h)
     cudaFree(h->counters);
     cudaFree(h->stamps);
     cudaFree(h->rhok_partials);
+    if (h->fault_host)
+        cudaFreeHost(h->fault_host);
     free(h);
     return 0;
     }
 
 uint64_t cavb200_launch_count(const cavb200_handle* h) { return h ? h->launches : 0; }
+uint64_t cavb200_fault_count(const cavb200_handle* h) { return h ? h->faults : 0; }
 
 int cavb200_debug_stamps(cavb200_handle* h, uint64_t* out, uint32_t n_ctas)
     {
@@ -220,6 +255,8 @@ int cavb200_force(cavb200_handle* h, const double* pos, const double* charge, co
     {
     if (!h)
         return (int)cudaErrorInvalidValue;
+    if (const int fault = check_fault(h))
+        return fault;
     if (N == 0)
         return 0;
     ForceIn f;
@@ -234,6 +271,8 @@ int cavb200_force_rank1(cavb200_handle* h, const double* pos, const double* char
     {
     if (!h)
         return (int)cudaErrorInvalidValue;
+    if (const int fault = check_fault(h))
+        return fault;
     if (N == 0)
         return 0;
     ForceIn f;
@@ -271,7 +310,7 @@ int cavb200_force_read(cavb200_handle* h, double energies[3], double dipole[3], 
     Scalars s;
     CAVB_CHECK(cudaMemcpyAsync(&s, h->scalars, sizeof(Scalars), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CAVB_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
-    if (s.err == 2.0)
+    if (s.err_force == 2.0)
         return (int)cudaErrorLaunchTimeout;
     for (int k = 0; k < 3; k++)
         {
@@ -291,6 +330,8 @@ int cavb200_bussi(cavb200_handle* h, double* vel, const uint32_t* group_idx, uin
     {
     if (!h || !args)
         return (int)cudaErrorInvalidValue;
+    if (const int fault = check_fault(h))
+        return fault;
     if (args->deltaT == 0.0) // BussiReservoirThermostat.h:45-48: {1,1}, nothing else happens
         return 0;
     BussiIn b;
@@ -305,6 +346,8 @@ int cavb200_bussi_ke(cavb200_handle* h, const double* vel, const uint32_t* group
     {
     if (!h)
         return (int)cudaErrorInvalidValue;
+    if (const int fault = check_fault(h))
+        return fault;
     BussiIn b;
     int rc = fill_bussi(b, const_cast<double*>(vel), group_idx, group_first, n, nullptr, 0);
     if (rc)
@@ -344,6 +387,8 @@ int cavb200_step(cavb200_handle* h, const double* pos, const double* charge, con
     {
     if (!h || !bussi)
         return (int)cudaErrorInvalidValue;
+    if (const int fault = check_fault(h))
+        return fault;
     if (N == 0)
         return 0;
     if ((unsigned long long)group_first + n_group > N)

@@ -68,8 +68,12 @@ struct __align__(16) Scalars
     double alpha;
     double inst;         // instantaneous reservoir energy  KE (1 - alpha^2)
     double cumulative;   // running sum of inst
-    double err;          // 0 ok, 1 = zero kinetic energy with dof != 0, 2 = barrier timeout
-    double pad1[3];
+    double err;          // thermostat status of the LAST call that published KE / alpha: 0 ok, 1 = zero kinetic energy with dof != 0, 2 = hand-off timeout
+    double err_force;    // cavity-force status of the LAST call that published a dipole: 0 ok, 2 = hand-off timeout
+    // host-mapped (pinned) word a kernel sets when a hand-off between co-resident CTAs timed out; the host looks at it
+    // at the top of every compute call without any synchronisation (api.cu check_fault)
+    unsigned long long* fault;
+    double pad1[1];
     };
 
 struct Tuning
@@ -78,7 +82,9 @@ struct Tuning
     int threads;         // CTA size of the streaming kernels (256 / 512 / 1024)
     int ctas_per_sm;     // resident CTAs per SM the grid is sized for
     int unroll;          // independent particle loads in flight per thread (1, 2 or 4)
-    int pdl;             // launch with programmatic stream serialization (hides the launch gap)
+    int pdl;             // 1: launch with programmatic stream serialization (hides the launch gap; co-residency of the persistent
+                         //    grids by construction on a device this stream has to itself); 0: cooperative launch (the driver
+                         //    guarantees co-residency, ~2 us per launch slower).  Switched to 0 by the library after a fault.
     int stamps;          // debug: record per-CTA phase timestamps of the cooperative kernel
     int md_shape;        // cavb200_md_step_fused launch shape: 0 = one 768-thread CTA per SM (default), 1 = two 384-thread CTAs
     int auto_threads;    // step kernel: pick 320 / 352 / 384 threads per CTA from the particle count (1) or use `threads` (0)
@@ -110,6 +116,8 @@ struct cavb200_handle
     cavb::Scalars* scalars;           // 1 record
     unsigned long long* counters;     // [2] hand-off epoch, [4] reduce-pass ticket, [8..] Final (variant 0), [32..] Final (rank-1)
     uint64_t launches;
+    uint64_t faults;                  // hand-off timeouts seen so far (each one switched the handle to cooperative launches)
+    unsigned long long* fault_host;   // pinned + mapped: the word Scalars::fault points at
     unsigned long long* stamps;       // MAX_PARTIALS x 8 timestamps (debug)
     cavb::Tuning tune;
     cavb::ShardState shard;
@@ -213,6 +221,13 @@ __device__ __forceinline__ unsigned long long atom_acq_rel_add_u64(unsigned long
 // NOTE (measured, round 1): polling with a weak ld.global.cg does NOT work on sm_100 -- a thread
 // whose first poll missed kept reading the stale value until the 2 s guard fired.  Polls and record
 // reads therefore use strong (relaxed, gpu-scope) loads.
+// a hand-off timed out: tell the host (system-scope store into pinned memory; cold path)
+__device__ __forceinline__ void raise_fault(const Scalars* s)
+    {
+    unsigned long long* f = s->fault;
+    if (f)
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(1ull) : "memory");
+    }
 __device__ __forceinline__ unsigned long long globaltimer_ns()
     {
     unsigned long long t;
@@ -287,4 +302,7 @@ inline const Final* rank1_final(const cavb200_handle* h) { return reinterpret_ca
 void fill_bussi_constants(BussiIn& b, const cavb200_bussi_args* a);
 int launch_hotpath(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cudaStream_t s);
 int launch_shard_step(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cudaStream_t s);
+// top of every compute entry point: a hand-off timeout reported by an earlier launch (Scalars::fault) switches the handle
+// to cooperative launches for good and is returned ONCE as cudaErrorLaunchTimeout
+int check_fault(cavb200_handle* h);
     } // namespace cavb

@@ -164,7 +164,7 @@ extern "C" int cavb200_step_host_wait(cavb200_handle* h, uint32_t slot, double e
         bussi_out[3] = s.cumulative;
         bussi_out[4] = s.err;
         }
-    if (s.err == 2.0)
+    if (s.err == 2.0 || s.err_force == 2.0)
         return (int)cudaErrorLaunchTimeout;
     return 0;
     }

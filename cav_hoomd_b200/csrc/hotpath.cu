@@ -111,7 +111,11 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     if (blockIdx.x == 0 && threadIdx.x == 0)
         *epoch_ctr = epoch;
     if (sc.fin.timeout)
+        {
+        if (threadIdx.x == 0)
+            raise_fault(scalars); // outputs not written; the host sees it at its next call (api.cu check_fault)
         return;
+        }
     // from here on the next kernel's CTAs may take the SMs this grid's CTAs leave
     pdl_launch_dependents();
     if (PREF)
@@ -179,7 +183,11 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     if (blockIdx.x == 0 && threadIdx.x == 0)
         *epoch_ctr = epoch; // every CTA has published twice, hence read the counter
     if (sc.fin.timeout || timeout_f)
+        {
+        if (threadIdx.x == 0)
+            raise_fault(scalars);
         return;
+        }
     pdl_launch_dependents();
     apply_phase<false, true, UNROLL>(sc.fin, f, b);
     if (my_stamps)
@@ -331,7 +339,11 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         if (my_stamps)
             my_stamps[5] = globaltimer_ns();
         if (finF.timeout || finK.timeout)
+            {
+            if (threadIdx.x == 0)
+                raise_fault(scalars);
             return;
+            }
         pdl_launch_dependents();
         if (contiguous)
             {
@@ -354,7 +366,11 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         if (my_stamps)
             my_stamps[5] = globaltimer_ns();
         if (finF.timeout || finK.timeout)
+            {
+            if (threadIdx.x == 0)
+                raise_fault(scalars);
             return;
+            }
         pdl_launch_dependents();
         apply_phase<true, false, UNROLL>(finF, f, b, g);
         }

@@ -196,40 +196,70 @@ __device__ __forceinline__ StreamGrid whole_grid()
     return g;
     }
 
+// Kinetic-energy pass over a group given as an index list (what HOOMD's ParticleGroup hands out) or as a window
+// [first, first + n).  With a list, element j needs gidx[j] before its velocity can be fetched: two dependent memory
+// round trips per loop iteration as first written (18.0 vs 16.1 us per 1M-particle Bussi call, profiles/ab_r2b.txt).
+// The index loads are therefore software-pipelined one iteration ahead -- the indices of iteration i+1 are requested
+// together with the velocities of iteration i -- so only the first iteration pays the second round trip.
 template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const BussiIn& b, const StreamGrid g = whole_grid())
     {
+    constexpr int U = UNROLL > 1 ? UNROLL : 1;
     const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
     unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     const unsigned long long n = b.n;
-    double ke[UNROLL > 1 ? UNROLL : 1];
+    double ke[U];
 #pragma unroll
-    for (int k = 0; k < (UNROLL > 1 ? UNROLL : 1); k++)
+    for (int k = 0; k < U; k++)
         ke[k] = 0.0;
-    if (UNROLL > 1)
+    if (b.gidx)
         {
-        for (; j + (UNROLL - 1) * stride < n; j += UNROLL * stride)
-            {
-            double4 v[UNROLL];
+        unsigned int nxt[U];
 #pragma unroll
-            for (int k = 0; k < UNROLL; k++)
+        for (int k = 0; k < U; k++)
+            nxt[k] = (j + k * stride < n) ? __ldg(b.gidx + j + k * stride) : 0u;
+        for (; j < n; j += U * stride)
+            {
+            double4 v[U];
+            unsigned int cur[U];
+#pragma unroll
+            for (int k = 0; k < U; k++)
                 {
-                const unsigned long long jj = j + k * stride;
-                const unsigned long long idx = b.gidx ? (unsigned long long)__ldg(b.gidx + jj) : b.first + jj;
-                v[k] = ld256(b.vel + idx);
+                cur[k] = nxt[k];
+                v[k] = make_double4(0.0, 0.0, 0.0, 0.0);
+                if (j + k * stride < n)
+                    v[k] = ld256(b.vel + cur[k]);
                 }
 #pragma unroll
-            for (int k = 0; k < UNROLL; k++)
-                ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z);
+            for (int k = 0; k < U; k++)
+                {
+                const unsigned long long jn = j + (U + k) * stride;
+                nxt[k] = jn < n ? __ldg(b.gidx + jn) : 0u;
+                }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z); // (+0 for the padding slots)
             }
         }
-    for (; j < n; j += stride)
+    else
         {
-        const unsigned long long idx = b.gidx ? (unsigned long long)__ldg(b.gidx + j) : b.first + j;
-        const double4 v = ld256(b.vel + idx);
-        ke[0] += v.w * (v.x * v.x + v.y * v.y + v.z * v.z);
+        for (; j + (U - 1) * stride < n; j += U * stride)
+            {
+            double4 v[U];
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                v[k] = ld256(b.vel + b.first + j + k * stride);
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z);
+            }
+        for (; j < n; j += stride)
+            {
+            const double4 v = ld256(b.vel + b.first + j);
+            ke[0] += v.w * (v.x * v.x + v.y * v.y + v.z * v.z);
+            }
         }
 #pragma unroll
-    for (int k = 0; k < (UNROLL > 1 ? UNROLL : 1); k++)
+    for (int k = 0; k < U; k++)
         a.ke += ke[k];
     }
 
@@ -834,6 +864,7 @@ __device__ __forceinline__ void finalize(const ForceIn& f, const BussiIn& b, Blo
             scalars->Dq[1] = fin.Dq[1];
             scalars->photon_idx = fin.has_photon ? (long long)first : -1;
             scalars->n_L = (unsigned int)m.n_L;
+            scalars->err_force = fin.timeout ? 2.0 : 0.0; // written by every call, so one failure does not stick
             }
         if (BUSSI)
             {
@@ -843,12 +874,11 @@ __device__ __forceinline__ void finalize(const ForceIn& f, const BussiIn& b, Blo
                 scalars->alpha = fin.alpha;
                 scalars->inst = inst;
                 scalars->cumulative = __dadd_rn(scalars->cumulative, inst); // :90
-                if (!fin.bussi_ok)
-                    scalars->err = 1.0;
                 }
+            scalars->err = fin.timeout ? 2.0 : (fin.bussi_ok ? 0.0 : 1.0);
             }
         if (fin.timeout)
-            scalars->err = 2.0;
+            raise_fault(scalars);
         }
     }
 
@@ -906,40 +936,68 @@ __device__ __forceinline__ void apply_force(const Final& fin, const ForceIn& f, 
 template<int UNROLL>
 __device__ __forceinline__ void apply_rescale(double alpha, const BussiIn& b, const StreamGrid g = whole_grid())
     {
+    constexpr int U = UNROLL > 1 ? UNROLL : 1;
     const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
     unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     const unsigned long long n = b.n;
-    if (UNROLL > 1)
+    if (b.gidx)
         {
-        for (; j + (UNROLL - 1) * stride < n; j += UNROLL * stride)
+        // index list: indices fetched one iteration ahead (see reduce_ke)
+        unsigned int nxt[U];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            nxt[k] = (j + k * stride < n) ? __ldg(b.gidx + j + k * stride) : 0u;
+        for (; j < n; j += U * stride)
             {
-            double4 v[UNROLL];
-            unsigned long long idx[UNROLL];
+            double4 v[U];
+            unsigned int cur[U];
 #pragma unroll
-            for (int k = 0; k < UNROLL; k++)
+            for (int k = 0; k < U; k++)
                 {
-                const unsigned long long jj = j + k * stride;
-                idx[k] = b.gidx ? (unsigned long long)__ldg(b.gidx + jj) : b.first + jj;
-                v[k] = ld256(b.vel + idx[k]);
+                cur[k] = nxt[k];
+                if (j + k * stride < n)
+                    v[k] = ld256(b.vel + cur[k]);
                 }
 #pragma unroll
-            for (int k = 0; k < UNROLL; k++)
+            for (int k = 0; k < U; k++)
                 {
-                v[k].x = __dmul_rn(v[k].x, alpha);
-                v[k].y = __dmul_rn(v[k].y, alpha);
-                v[k].z = __dmul_rn(v[k].z, alpha);
-                st256(b.vel + idx[k], v[k]);
+                const unsigned long long jn = j + (U + k) * stride;
+                nxt[k] = jn < n ? __ldg(b.gidx + jn) : 0u;
                 }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                if (j + k * stride < n)
+                    {
+                    v[k].x = __dmul_rn(v[k].x, alpha);
+                    v[k].y = __dmul_rn(v[k].y, alpha);
+                    v[k].z = __dmul_rn(v[k].z, alpha);
+                    st256(b.vel + cur[k], v[k]);
+                    }
+            }
+        return;
+        }
+    for (; j + (U - 1) * stride < n; j += U * stride)
+        {
+        double4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            v[k] = ld256(b.vel + b.first + j + k * stride);
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            {
+            v[k].x = __dmul_rn(v[k].x, alpha);
+            v[k].y = __dmul_rn(v[k].y, alpha);
+            v[k].z = __dmul_rn(v[k].z, alpha);
+            st256(b.vel + b.first + j + k * stride, v[k]);
             }
         }
     for (; j < n; j += stride)
         {
-        const unsigned long long idx = b.gidx ? (unsigned long long)__ldg(b.gidx + j) : b.first + j;
-        double4 v = ld256(b.vel + idx);
+        double4 v = ld256(b.vel + b.first + j);
         v.x = __dmul_rn(v.x, alpha);
         v.y = __dmul_rn(v.y, alpha);
         v.z = __dmul_rn(v.z, alpha);
-        st256(b.vel + idx, v);
+        st256(b.vel + b.first + j, v);
         }
     }
 

@@ -73,8 +73,7 @@ __global__ void __launch_bounds__(256)
                     scalars->inst = inst;
                     scalars->cumulative = __dadd_rn(scalars->cumulative, inst);
                     }
-                else
-                    scalars->err = 1.0; // zero kinetic energy with dof != 0 (:57-61): no rescale
+                scalars->err = ok ? 0.0 : 1.0; // 1: zero kinetic energy with dof != 0 (:57-61), no rescale
                 }
             }
         s_alpha = alpha;
@@ -192,8 +191,7 @@ __global__ void __launch_bounds__(256, 3)
                     scalars->inst = inst;
                     scalars->cumulative = __dadd_rn(scalars->cumulative, inst);
                     }
-                else
-                    scalars->err = 1.0;
+                scalars->err = ok ? 0.0 : 1.0;
                 }
             }
         s_alpha = alpha;
@@ -381,7 +379,11 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     // (polling with 16 ns instead of 300 ns sleeps was measured here too: 35.92 vs 35.76 us, no better)
     const Final finK = take_final<false>(finals + 1, epoch, prefetch_final<false>(finals + 1));
     if (finK.timeout)
+        {
+        if (threadIdx.x == 0)
+            raise_fault(scalars);
         return;
+        }
     const double alpha = (b.rescale && finK.bussi_ok) ? finK.alpha : 1.0;
     // pass 2: v2 = alpha v1 + dt/2 f/m, r += dt v2, dipole term of the new position (U2 particles in flight per thread)
     Acc a;
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
             {
             const unsigned long long j = i + k * stride;
             v[k] = ld256(vel + j);
-            p[k] = ld256_stream(pos + j);
+            p[k] = ld256_na(pos + j); // coherent: this kernel overwrites pos (no .nc)
             c[k] = __ldg(r1.charge + j);
             ix[k] = __ldg(fnew.image + 3 * j + 0);
             iy[k] = __ldg(fnew.image + 3 * j + 1);
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
             fc.y = __dadd_rn(fo.y, fc.y);
             fc.z = __dadd_rn(fo.z, fc.z);
             }
-        finish(i, ld256(vel + i), ld256_stream(pos + i), c, __ldg(fnew.image + 3 * i + 0), __ldg(fnew.image + 3 * i + 1),
+        finish(i, ld256(vel + i), ld256_na(pos + i), c, __ldg(fnew.image + 3 * i + 0), __ldg(fnew.image + 3 * i + 1),
                __ldg(fnew.image + 3 * i + 2), fc);
         }
     block_merge<true, false>(a, fnew, sc);
@@ -721,6 +723,8 @@ extern "C" int cavb200_md_step_fused(cavb200_handle* h, double* pos, double* vel
         return (int)cudaErrorMisalignedAddress;
     if (!h->coop_supported)
         return (int)cudaErrorNotSupported;
+    if (const int fault = check_fault(h))
+        return fault;
     Rank1In r;
     int rc = fill_rank1(h, r, charge, pos, L_typeid, params->couplstr);
     if (rc)

@@ -458,7 +458,10 @@ class ComputeThermo
     Scalar getTranslationalDOF() const { return m_group->getTranslationalDOF(); }
     Scalar getRotationalDOF() const { return m_group->getRotationalDOF(); }
     Scalar getTranslationalKineticEnergy() const { return m_ke; }
-    Scalar getRotationalKineticEnergy() const { return 0; }
+    //! rotational kinetic energy: HOOMD forms it from angular momenta and moments of inertia (upstream code);
+    //! the shim makes it an injected input, like the random draws
+    Scalar getRotationalKineticEnergy() const { return m_rke; }
+    void setRotationalKineticEnergy(Scalar rke) { m_rke = rke; }
     Scalar getTranslationalTemperature() const
         {
         return getTranslationalDOF() > 0 ? 2.0 * m_ke / getTranslationalDOF() : 0.0;
@@ -469,6 +472,7 @@ class ComputeThermo
     std::shared_ptr<SystemDefinition> m_sysdef;
     std::shared_ptr<ParticleGroup> m_group;
     Scalar m_ke;
+    Scalar m_rke = 0;
     };
     } // namespace md
 

@@ -32,10 +32,16 @@
  *   - a handle owns its workspace and is bound to one device; calls on one handle must be issued
  *     from one host thread at a time (HOOMD's integrator thread).
  *   - the force / Bussi / step / md_step_fused / shard kernels are PERSISTENT: their grids fill the device and the CTAs
- *     hand results to each other while resident.  Issue them so that no two of them (of this or of another handle) can
- *     run at the same time on one device -- one stream, as HOOMD does, or streams ordered by events (what
- *     cavb200_step_host_submit does internally).  If co-residency fails anyway the hand-off gives up after 50 ms: the
- *     call's outputs are not written, the *_read calls return cudaErrorLaunchTimeout / err = 2; nothing hangs.
+ *     hand results to each other while resident.  By default they are launched with programmatic stream serialization
+ *     (the next call's CTAs start while this call drains), which relies on the stream having the device to itself --
+ *     one stream, as HOOMD does, or streams ordered by events (what cavb200_step_host_submit does internally).  If
+ *     something else holds SM slots (another stream, another process under MPS) and a grid is not co-resident, the
+ *     hand-off gives up after 50 ms: nothing hangs, that call's outputs are NOT written, the kernel raises a fault word
+ *     in pinned host memory, and the NEXT compute call on the handle returns cudaErrorLaunchTimeout once (the plugin
+ *     classes throw) and switches the handle to cooperative launches for good -- the driver then guarantees
+ *     co-residency, at ~2 us per launch.  cavb200_set_tuning(h, "pdl", 0) selects cooperative launches from the start
+ *     (use it when the GPU is shared).  The *_read calls of the failed call also return cudaErrorLaunchTimeout /
+ *     err = 2; the status words are rewritten by every call, so one failure does not stick.
  */
 #ifndef CAVB200_H
 #define CAVB200_H
@@ -88,6 +94,8 @@ int cavb200_destroy(cavb200_handle* h);
 const char* cavb200_error_string(int err);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t cavb200_launch_count(const cavb200_handle* h);
+/* Number of hand-off timeouts this handle has seen (see the conventions above); 0 in a healthy run. */
+uint64_t cavb200_fault_count(const cavb200_handle* h);
 /* Debug: with tuning "stamps" = 1 the cooperative kernel records, per CTA, globaltimer ns at
  * {start, after reduce, after barrier, after combine, after apply}; out = uint64[8*n_ctas]. */
 int cavb200_debug_stamps(cavb200_handle* h, uint64_t* out, uint32_t n_ctas);

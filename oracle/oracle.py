@@ -163,6 +163,9 @@ class RefOracle:
         L.ref_bussi_destroy.argtypes = [C.c_void_p]
         L.ref_bussi_step.restype = C.c_int
         L.ref_bussi_step.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_double, _dp]
+        if hasattr(L, "ref_bussi_step_rot"):
+            L.ref_bussi_step_rot.restype = C.c_int
+            L.ref_bussi_step_rot.argtypes = [C.c_void_p, C.c_uint64, C.c_double, _dp, C.c_double, C.c_double, _dp]
         L.ref_bussi_read.argtypes = [C.c_void_p, _dp]
         L.ref_bussi_reset.argtypes = [C.c_void_p]
 
@@ -196,6 +199,17 @@ class RefOracle:
         if rc != 0:
             raise RuntimeError("Bussi thermostat requires non-zero initial momenta.")
         return dict(alpha=out[0], ke=out[1], cumulative=out[2], instantaneous=out[3])
+
+    def bussi_step_rot(self, h, timestep, dt, draws, rot_dof, rot_ke):
+        """getRescalingFactorsOne with rotational degrees of freedom (reference
+        src/BussiReservoirThermostat.h:53-55,77-95); draws = [normal_t, gamma_t, normal_r, gamma_r]."""
+        out = np.zeros(7)
+        d = np.ascontiguousarray(draws, dtype=np.float64)
+        rc = self.lib.ref_bussi_step_rot(h, timestep, dt, _d(d), rot_dof, rot_ke, _d(out))
+        if rc < 0:
+            raise RuntimeError("Bussi thermostat requires non-zero initial momenta.")
+        return dict(alpha=out[0], alpha_rot=out[1], ke=out[2], cumulative=out[3], instantaneous=out[4],
+                    cumulative_rot=out[5], instantaneous_rot=out[6], draws_left=rc)
 
     def bussi_read(self, h, N):
         v = np.empty((N, 4))

@@ -180,6 +180,42 @@ int ref_bussi_step(void* h, uint64_t timestep, double deltaT, double r_normal, d
     return 0;
     }
 
+// The same with rotational degrees of freedom (reference src/BussiReservoirThermostat.h:53-55,77-81,87-95): the
+// rotational dof / kinetic energy are injected (HOOMD's ComputeThermo forms them upstream); draws = {normal_t, gamma_t,
+// normal_r, gamma_r} in the order the reference consumes them.  out = {alpha_t, alpha_r, KE_t, cumulative_t,
+// instantaneous_t, cumulative_r, instantaneous_r}.  Velocities are not touched.
+int ref_bussi_step_rot(void* h, uint64_t timestep, double deltaT, const double draws[4], double rot_dof, double rot_ke,
+                       double out[7])
+    {
+    auto* r = static_cast<RefBussi*>(h);
+    r->group->setRotationalDOF(rot_dof);
+    r->thermo->setRotationalKineticEnergy(rot_ke);
+    auto& q = RandomGenerator::injected();
+    q.clear();
+    for (int k = 0; k < 4; k++)
+        q.push_back(draws[k]);
+    std::array<Scalar, 2> f;
+    try
+        {
+        f = r->th->getRescalingFactorsOne(timestep, deltaT);
+        }
+    catch (const std::exception&)
+        {
+        q.clear();
+        return -2;
+        }
+    const int left = (int)q.size();
+    q.clear();
+    out[0] = f[0];
+    out[1] = f[1];
+    out[2] = r->thermo->getTranslationalKineticEnergy();
+    out[3] = r->th->getReservoirEnergyTranslational();
+    out[4] = r->th->getInstantaneousReservoirTranslational();
+    out[5] = r->th->getReservoirEnergyRotational();
+    out[6] = r->th->getInstantaneousReservoirRotational();
+    return left; // draws NOT consumed (dof <= 1 draws no gamma, dof == 0 draws nothing)
+    }
+
 void ref_bussi_read(void* h, double* vel4)
     {
     auto* r = static_cast<RefBussi*>(h);

@@ -86,12 +86,14 @@ PYBIND11_MODULE(_hoomd_shim, m)
         .def(py::init<std::shared_ptr<SystemDefinition>, const std::vector<unsigned int>&>())
         .def("getNumMembers", &ParticleGroup::getNumMembers)
         .def("setTranslationalDOF", &ParticleGroup::setTranslationalDOF)
+        .def("setRotationalDOF", &ParticleGroup::setRotationalDOF)
         .def("getTranslationalDOF", &ParticleGroup::getTranslationalDOF);
 
     py::class_<md::ComputeThermo, std::shared_ptr<md::ComputeThermo>>(m, "ComputeThermo")
         .def(py::init<std::shared_ptr<SystemDefinition>, std::shared_ptr<ParticleGroup>>())
         .def("compute", &md::ComputeThermo::compute)
-        .def("getTranslationalKineticEnergy", &md::ComputeThermo::getTranslationalKineticEnergy);
+        .def("getTranslationalKineticEnergy", &md::ComputeThermo::getTranslationalKineticEnergy)
+        .def("setRotationalKineticEnergy", &md::ComputeThermo::setRotationalKineticEnergy);
 
     py::class_<md::Thermostat, std::shared_ptr<md::Thermostat>>(m, "Thermostat")
         .def("getRescalingFactorsOne", &md::Thermostat::getRescalingFactorsOne)

@@ -35,6 +35,8 @@ void export_BussiReservoirThermostat(pybind11::module& m)
     cls.def_property("kT", &Self::getT, &Self::setT);
     cls.def_property("tau", &Self::getTau, &Self::setTau);
     cls.def_property("fused_rescale", &Self::getFusedRescale, &Self::setFusedRescale);
+    cls.def_property("cooperative_launch", &Self::getCooperativeLaunch, &Self::setCooperativeLaunch);
+    cls.def("getFaultCount", &Self::getFaultCount);
     for (const Getter& g : reservoir_getters)
         cls.def(g.name, g.fn);
     cls.def("resetReservoirEnergy", &Self::resetReservoirEnergy);

@@ -43,6 +43,12 @@ class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat
                              std::shared_ptr<ComputeThermo> thermo, std::shared_ptr<SystemDefinition> sysdef, Scalar tau)
         : Thermostat(T, group, thermo, sysdef), m_tau(tau), m_handle(nullptr), m_fused(false), m_stale(false)
         {
+#ifdef ENABLE_MPI
+        // the kinetic energy is reduced over THIS rank's particles only, where ComputeThermo all-reduces
+        // (reference :50-55 under domain decomposition): refuse rather than thermostat with a wrong alpha
+        if (m_sysdef->isDomainDecomposed())
+            throw std::runtime_error("BussiReservoirThermostat (cavb200): domain-decomposed (multi-rank) runs are not supported");
+#endif
         int device = 0;
 #ifdef ENABLE_HIP
         cudaGetDevice(&device);
@@ -61,27 +67,43 @@ class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat
 
         const Scalar translational_dof = m_group->getTranslationalDOF();
         const Scalar rotational_dof = m_group->getRotationalDOF();
-        if (rotational_dof != 0)
-            throw std::runtime_error("BussiReservoirThermostat (cavb200): rotational degrees of freedom are not supported");
 
-        // same generator, same seeding, same draw order as the reference (:63-67, :192-200):
-        // the draws do not depend on the kinetic energy, so they are made before the launch
+        // Rotational degrees of freedom (anisotropic bodies; 0 for the point particles of every shipped example):
+        // the rotational kinetic energy is HOOMD's own quantity (angular momenta, moments of inertia), so it comes
+        // from ComputeThermo exactly as in the reference (:50-55) -- only then is the full thermo pass paid for.
+        Scalar rotational_kinetic_energy = 0.0;
+        if (rotational_dof != 0)
+            {
+            m_thermo->compute(timestep);
+            rotational_kinetic_energy = m_thermo->getRotationalKineticEnergy();
+            if (rotational_kinetic_energy == 0) // reference :57-61
+                throw std::runtime_error("Bussi thermostat requires non-zero initial momenta.");
+            }
+
+        // same generator, same seeding, same draw order as the reference (:63-67, :192-200: translational normal,
+        // translational gamma, rotational normal, rotational gamma).  The draws do not depend on the kinetic
+        // energies, so they are made before the launch.
         unsigned int instance_id = 0;
         if (m_group->getNumMembersGlobal() > 0)
             instance_id = m_group->getMemberTag(0);
         RandomGenerator rng(Seed(RNGIdentifier::BussiThermostat, timestep, m_sysdef->getSeed()), instance_id);
         const Scalar set_T = m_T->operator()(timestep);
         double r_normal = 0.0, gamma_draw = 0.0;
-        if (translational_dof != 0)
+        draw(rng, translational_dof, r_normal, gamma_draw);
+        double r_normal_rot = 0.0, gamma_draw_rot = 0.0;
+        draw(rng, rotational_dof, r_normal_rot, gamma_draw_rot);
+
+        Scalar rotational_factor = 1.0;
+        if (rotational_dof != 0)
             {
-            NormalDistribution<double> normal(1.0);
-            r_normal = normal(rng);
-            if (translational_dof > 1.0)
-                {
-                GammaDistribution<double> gamma((translational_dof - 1.0) / Scalar(2.0), Scalar(1.0));
-                gamma_draw = gamma(rng);
-                }
+            rotational_factor
+                = compute_rescale_factor(rotational_kinetic_energy, rotational_dof, deltaT, set_T, r_normal_rot, gamma_draw_rot);
+            const Scalar delta_rot = rotational_kinetic_energy * (1.0 - rotational_factor * rotational_factor); // :87
+            m_reservoir_energy_rotational += delta_rot;                                                        // :91
+            m_instantaneous_reservoir_rotational = delta_rot;                                                  // :95
             }
+        else
+            m_instantaneous_reservoir_rotational = 0.0; // :87 with KE = 0
 
         auto pdata = m_sysdef->getParticleData();
         ArrayHandle<Scalar4> d_vel(pdata->getVelocities(), access_location::device,
@@ -94,7 +116,7 @@ class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat
             cavb200_bussi_args a = {set_T, m_tau, deltaT, translational_dof, r_normal, gamma_draw};
             check(cavb200_bussi(m_handle, reinterpret_cast<double*>(d_vel.data), d_index.data, 0, n, &a, nullptr));
             m_stale = true; // reservoir energies live on the device until a getter asks
-            return {1.0, 1.0};
+            return {1.0, rotational_factor};
             }
 
         check(cavb200_bussi_ke(m_handle, reinterpret_cast<const double*>(d_vel.data), d_index.data, 0, n, nullptr));
@@ -108,14 +130,23 @@ class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat
         m_host_cumulative += delta; // reference :90
         m_reservoir_energy_translational = m_host_cumulative + m_dev_cumulative;
         m_instantaneous_reservoir_translational = delta;
-        m_instantaneous_reservoir_rotational = 0.0;
-        return {factor, 1.0};
+        return {factor, rotational_factor};
         }
 
     Scalar getTau() const { return m_tau; }
     void setTau(Scalar tau) { m_tau = tau; }
     bool getFusedRescale() const { return m_fused; }
     void setFusedRescale(bool f) { m_fused = f; }
+    //! true: cooperative launches (safe when the GPU is shared with other streams / processes); false (default):
+    //! programmatic dependent launches (include/cavb200.h, conventions)
+    bool getCooperativeLaunch() const
+        {
+        int pdl = 1;
+        cavb200_get_tuning(m_handle, "pdl", &pdl);
+        return pdl == 0;
+        }
+    void setCooperativeLaunch(bool c) { cavb200_set_tuning(m_handle, "pdl", c ? 0 : 1); }
+    unsigned long long getFaultCount() const { return cavb200_fault_count(m_handle); }
 
     Scalar getReservoirEnergyTranslational() { sync(); return m_reservoir_energy_translational; }
     Scalar getReservoirEnergyRotational() { return m_reservoir_energy_rotational; }
@@ -164,8 +195,25 @@ class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat
         }
 
     private:
+    //! one degree-of-freedom class's draws, in the reference's order (:192-200); nothing is drawn for dof == 0 (:181-184)
+    static void draw(RandomGenerator& rng, Scalar dof, double& r_normal, double& gamma_draw)
+        {
+        if (dof == 0)
+            return;
+        NormalDistribution<double> normal(1.0);
+        r_normal = normal(rng);
+        if (dof > 1.0)
+            {
+            GammaDistribution<double> gamma((dof - 1.0) / Scalar(2.0), Scalar(1.0));
+            gamma_draw = gamma(rng);
+            }
+        }
     void check(int err) const
         {
+        if (err == 702) // cudaErrorLaunchTimeout: see include/cavb200.h, conventions
+            throw std::runtime_error("BussiReservoirThermostat: an earlier thermostat kernel could not run with its whole grid "
+                                     "resident (the GPU is shared with another stream or process), so that step's "
+                                     "velocities were not rescaled; the thermostat now uses cooperative launches");
         if (err)
             throw std::runtime_error(std::string("BussiReservoirThermostat: ") + cavb200_error_string(err));
         }

@@ -13,6 +13,11 @@ namespace
     {
 void check(int err, const char* what)
     {
+    if (err == 702) // cudaErrorLaunchTimeout: see include/cavb200.h, conventions
+        throw std::runtime_error(std::string("CavityForceComputeGPU: ") + what
+                                 + ": an earlier cavity-force kernel could not run with its whole grid resident (the GPU is "
+                                   "shared with another stream or process), so that step's forces were not written; the force "
+                                   "now uses cooperative launches");
     if (err != 0)
         throw std::runtime_error(std::string("CavityForceComputeGPU: ") + what + ": " + cavb200_error_string(err));
     }
@@ -25,6 +30,12 @@ CavityForceComputeGPU::CavityForceComputeGPU(std::shared_ptr<SystemDefinition> s
     m_exec_conf->msg->notice(5) << "Constructing CavityForceComputeGPU (cavb200)" << std::endl;
     if (!m_exec_conf->isCUDAEnabled())
         throw std::runtime_error("CavityForceComputeGPU requires a GPU execution configuration (no CPU fallback)");
+#ifdef ENABLE_MPI
+    // the dipole is summed over THIS rank's particles only (like the reference): refuse
+    // rather than compute a wrong force under domain decomposition
+    if (m_sysdef->isDomainDecomposed())
+        throw std::runtime_error("CavityForceComputeGPU (cavb200): domain-decomposed (multi-rank) runs are not supported");
+#endif
     setParams(omegac, couplstr, phmass);
     for (int k = 0; k < 3; k++)
         m_energies[k] = m_dipole[k] = 0.0;
@@ -84,7 +95,7 @@ void CavityForceComputeGPU::computeForces(uint64_t timestep)
     // HOOMD runs its kernels on the legacy default stream: stream 0 ordering is the contract
     check(cavb200_force(m_handle, reinterpret_cast<const double*>(d_pos.data), d_charge.data,
                         reinterpret_cast<const int32_t*>(d_image.data), reinterpret_cast<double*>(d_force.data), N, L.x,
-                        L.y, L.z, L_typeid, &m_params, nullptr),
+                        L.y, L.z, L_typeid, &m_params, m_stream),
           "cavb200_force");
     m_fresh = false; // no synchronisation here: energies are fetched when somebody asks
     }
@@ -94,7 +105,7 @@ void CavityForceComputeGPU::readBack()
     if (m_fresh)
         return;
     int32_t photon = -1;
-    check(cavb200_force_read(m_handle, m_energies, m_dipole, &photon, nullptr), "cavb200_force_read");
+    check(cavb200_force_read(m_handle, m_energies, m_dipole, &photon, m_stream), "cavb200_force_read");
     m_fresh = true;
     }
 
@@ -113,6 +124,15 @@ Scalar CavityForceComputeGPU::getDipoleSelfEnergy()
     readBack();
     return m_energies[2];
     }
+bool CavityForceComputeGPU::getCooperativeLaunch() const
+    {
+    int pdl = 1;
+    cavb200_get_tuning(m_handle, "pdl", &pdl);
+    return pdl == 0;
+    }
+void CavityForceComputeGPU::setCooperativeLaunch(bool c) { cavb200_set_tuning(m_handle, "pdl", c ? 0 : 1); }
+unsigned long long CavityForceComputeGPU::getFaultCount() const { return cavb200_fault_count(m_handle); }
+
 pybind11::tuple CavityForceComputeGPU::getDipole()
     {
     readBack();
@@ -126,7 +146,7 @@ void CavityForceComputeGPU::trackOpen(unsigned int capacity)
 
 void CavityForceComputeGPU::trackSetReference()
     {
-    check(cavb200_track_set_reference(m_handle, nullptr), "cavb200_track_set_reference");
+    check(cavb200_track_set_reference(m_handle, m_stream), "cavb200_track_set_reference");
     }
 
 void CavityForceComputeGPU::trackRecord(uint64_t timestep)
@@ -134,7 +154,7 @@ void CavityForceComputeGPU::trackRecord(uint64_t timestep)
     // asynchronous, ordered after this step's force kernel on HOOMD's stream; the photon's kinetic energy needs
     // the velocities, everything else is already on the device
     ArrayHandle<Scalar4> d_vel(m_pdata->getVelocities(), access_location::device, access_mode::read);
-    check(cavb200_track_record(m_handle, timestep, reinterpret_cast<const double*>(d_vel.data), m_pdata->getN(), nullptr),
+    check(cavb200_track_record(m_handle, timestep, reinterpret_cast<const double*>(d_vel.data), m_pdata->getN(), m_stream),
           "cavb200_track_record");
     }
 
@@ -143,7 +163,7 @@ pybind11::list CavityForceComputeGPU::trackRead(unsigned int max_records)
     std::vector<double> buf((size_t)max_records * CAVB200_TRACK_WORDS + 1);
     uint32_t n = 0;
     uint64_t total = 0;
-    check(cavb200_track_read(m_handle, buf.data(), max_records, &n, &total, nullptr), "cavb200_track_read");
+    check(cavb200_track_read(m_handle, buf.data(), max_records, &n, &total, m_stream), "cavb200_track_read");
     pybind11::list out;
     for (uint32_t r = 0; r < n; r++)
         {
@@ -171,6 +191,10 @@ void export_CavityForceComputeGPU(pybind11::module& m)
         .def("getCouplingEnergy", &CavityForceComputeGPU::getCouplingEnergy)
         .def("getDipoleSelfEnergy", &CavityForceComputeGPU::getDipoleSelfEnergy)
         .def("getDipole", &CavityForceComputeGPU::getDipole)
+        .def_property("cooperative_launch", &CavityForceComputeGPU::getCooperativeLaunch,
+                      &CavityForceComputeGPU::setCooperativeLaunch)
+        .def("getFaultCount", &CavityForceComputeGPU::getFaultCount)
+        .def_property("stream", &CavityForceComputeGPU::getStream, &CavityForceComputeGPU::setStream)
         .def("trackOpen", &CavityForceComputeGPU::trackOpen, pybind11::arg("capacity"))
         .def("trackSetReference", &CavityForceComputeGPU::trackSetReference)
         .def("trackRecord", &CavityForceComputeGPU::trackRecord, pybind11::arg("timestep"))

@@ -38,6 +38,15 @@ class PYBIND11_EXPORT CavityForceComputeGPU : public ForceCompute
     Scalar getDipoleSelfEnergy();
     //! total molecular dipole of the last step (not in the reference API; free with the reduction)
     pybind11::tuple getDipole();
+    //! true: cooperative launches (safe when the GPU is shared with other streams / processes); false (default):
+    //! programmatic dependent launches.  The library switches to cooperative by itself after a hand-off timeout.
+    bool getCooperativeLaunch() const;
+    void setCooperativeLaunch(bool c);
+    unsigned long long getFaultCount() const;
+    //! CUDA stream the force kernel is issued on, as an integer (cudaStream_t); 0 = the legacy default stream HOOMD's
+    //! own kernels run on (the default, and what a HOOMD run uses).  For harnesses that drive several objects at once.
+    void setStream(size_t stream) { m_stream = reinterpret_cast<void*>(stream); }
+    size_t getStream() const { return reinterpret_cast<size_t>(m_stream); }
 
     //! Device-side trackers: what DipoleAutocorrelation / CavityModeTracker / EnergyTracker of the
     //! reference get from a full cpu_local_snapshot every step (src/cavitymd/analysis.py:188,234,535,578,1327) is
@@ -58,6 +67,7 @@ class PYBIND11_EXPORT CavityForceComputeGPU : public ForceCompute
     double m_energies[3];
     double m_dipole[3];
     bool m_fresh; //!< host copies are current
+    void* m_stream = nullptr;
     };
 
 namespace detail

@@ -76,6 +76,28 @@ def main():
         bout[f"{name}/rows"] = np.array(rows)
         bout[f"{name}/vel_final"] = ref.bussi_read(h, s.N)
         ref.bussi_close(h)
+    # rotational degrees of freedom (reference src/BussiReservoirThermostat.h:53-55,77-81,87-95): injected rotational
+    # dof / kinetic energy, four draws in the reference's order; three consecutive steps per case
+    rot_cases = [("rot_n200", 200, synth.TAU_5PS, 3.0 * 200, 0.04), ("rot_n64_rdof1", 64, 12.0, 1.0, 3e-4),
+                 ("rot_n128_tau0", 128, 0.0, 2.0 * 128, 0.02)]
+    for name, n, tau, rdof, rke in rot_cases:
+        s = synth.make_system(n, replica=6)
+        dof = 3.0 * n - 3.0
+        kT, dt = synth.KT_100K, synth.DT_1FS
+        h = ref.bussi_open(s.vel, np.arange(n, dtype=np.uint32), dof, kT, tau)
+        draws = np.column_stack([rng.standard_normal(3), rng.gamma((dof - 1) / 2, size=3), rng.standard_normal(3),
+                                 rng.gamma(max((rdof - 1) / 2, 0.5), size=3)])
+        draws[2, 2] = -2.9  # strongly negative rotational normal draw
+        rows = []
+        for k in range(3):
+            r = ref.bussi_step_rot(h, k, dt, draws[k], rdof, rke * (1 + 0.1 * k))
+            rows.append([r["alpha"], r["alpha_rot"], r["ke"], r["cumulative"], r["instantaneous"], r["cumulative_rot"],
+                         r["instantaneous_rot"], r["draws_left"]])
+        bout[f"{name}/vel0"] = s.vel
+        bout[f"{name}/args"] = np.array([dof, kT, tau, dt, rdof, rke])
+        bout[f"{name}/draws"] = draws
+        bout[f"{name}/rows"] = np.array(rows)
+        ref.bussi_close(h)
     np.savez_compressed(os.path.join(HERE, "bussi.npz"), **bout)
 
     # F(k,t): the reference's own functions (compute_density_field, generate_fibonacci_sphere,

@@ -108,7 +108,34 @@ def test_serial_dipole_vs_exact(coracle):
 # ---- Bussi -------------------------------------------------------------------------------------
 def bussi_cases():
     g = gold("bussi.npz")
-    return sorted({k.split("/")[0] for k in g.files})
+    return sorted({k.split("/")[0] for k in g.files if not k.startswith("rot_")})
+
+
+def bussi_rot_cases():
+    g = gold("bussi.npz")
+    return sorted({k.split("/")[0] for k in g.files if k.startswith("rot_")})
+
+
+@pytest.mark.parametrize("case", bussi_rot_cases())
+def test_bussi_rotational_factor_matches_golden(coracle, case):
+    """Rotational rescale factor and its reservoir bookkeeping (reference src/BussiReservoirThermostat.h:53-55,
+    77-81,87-95): compute_rescale_factor applied a second time with the same generator -- the C restatement against
+    vectors minted from the reference's own translation unit."""
+    g = gold("bussi.npz")
+    dof, kT, tau, dt, rdof, rke = g[f"{case}/args"]
+    cum_t = cum_r = 0.0
+    for k, (rn, gm, rn_r, gm_r) in enumerate(g[f"{case}/draws"]):
+        row = g[f"{case}/rows"][k]
+        ke_r = rke * (1 + 0.1 * k)
+        a_t = coracle.bussi_rescale_factor(row[2], dof, dt, kT, tau, rn, gm)
+        a_r = coracle.bussi_rescale_factor(ke_r, rdof, dt, kT, tau, rn_r, gm_r)
+        assert a_t == row[0] and a_r == row[1]
+        inst_t, inst_r = row[2] * (1.0 - a_t * a_t), ke_r * (1.0 - a_r * a_r)
+        cum_t += inst_t
+        cum_r += inst_r
+        assert inst_t == row[4] and inst_r == row[6] and cum_t == row[3] and cum_r == row[5]
+        assert row[7] == (1.0 if rdof <= 1.0 else 0.0)  # dof <= 1 draws no gamma variate (:195-200)
+    assert (g[f"{case}/rows"][:, 1] < 0).any() or case == "rot_n200"
 
 
 @pytest.mark.parametrize("case", bussi_cases())

@@ -105,6 +105,48 @@ def test_bussi_reservoir_thermostat_class(mods, coracle, fused):
     assert th.getTotalReservoirEnergy() == 0.0 and th.getInstantaneousReservoirTotal() == 0.0
 
 
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("case", ["rot_n200", "rot_n64_rdof1", "rot_n128_tau0"])
+def test_bussi_thermostat_rotational_dof(mods, case, fused):
+    """Rotational degrees of freedom: alpha_r and the rotational reservoir from the same generator, after the
+    translational draws (reference src/BussiReservoirThermostat.h:53-55,77-81,87-95) -- against vectors minted from
+    the reference's own translation unit (tests/golden/make_golden.py)."""
+    shim, _, bus = mods
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bussi.npz"))
+    dof, kT, tau, dt, rdof, rke = g[f"{case}/args"]
+    vel0 = g[f"{case}/vel0"]
+    n = vel0.shape[0] - 1
+    s = synth.make_system(n, replica=6)
+    assert np.array_equal(s.vel, vel0)
+    sysdef, pd = make_sysdef(shim, s)
+    group = shim.ParticleGroup(sysdef, list(range(n)))
+    group.setTranslationalDOF(dof)
+    group.setRotationalDOF(rdof)
+    thermo = shim.ComputeThermo(sysdef, group)
+    th = bus.BussiReservoirThermostat(shim.VariantConstant(kT), group, thermo, sysdef, tau)
+    th.fused_rescale = fused
+    for k, d in enumerate(g[f"{case}/draws"]):
+        row = g[f"{case}/rows"][k]
+        thermo.setRotationalKineticEnergy(rke * (1 + 0.1 * k))
+        bus._inject_draws([float(x) for x in d])
+        factors = th.getRescalingFactorsOne(k, dt)
+        assert factors[1] == row[1]  # host formula, the reference's operation order: bitwise
+        assert th.getInstantaneousReservoirRotational() == row[6] and th.getReservoirEnergyRotational() == row[5]
+        if fused:
+            assert factors[0] == 1.0
+        else:
+            assert abs(factors[0] - row[0]) <= 1e-12 * abs(row[0])
+        # (the golden rows never rescale the velocities, so the translational KE is the same every step)
+        assert np.isclose(th.getInstantaneousReservoirTranslational(), row[4], rtol=1e-9, atol=1e-18)
+        if fused:  # undo the in-kernel rescale to stay on the golden trajectory
+            pd.setVelocities(s.vel)
+    # zero rotational kinetic energy with rotational dof: the reference throws (:57-61)
+    thermo.setRotationalKineticEnergy(0.0)
+    bus._inject_draws([0.1, 1.0, 0.1, 1.0])
+    with pytest.raises(RuntimeError, match="non-zero initial momenta"):
+        th.getRescalingFactorsOne(9, dt)
+
+
 def test_bussi_thermostat_zero_momenta_throws(mods):
     shim, _, bus = mods
     s = synth.make_system(100)
@@ -145,3 +187,46 @@ def test_cavity_force_class_device_side_tracker(mods):
     ke_ph = 0.5 * s.vel[-1, 3] * np.sum(s.vel[-1, :3] ** 2)
     assert abs(rows[-1][11] - ke_ph) <= 1e-12 * ke_ph and int(rows[-1][15]) == s.N - 1
     assert rows[-1][7] == fc.getHarmonicEnergy()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("cooperative", [False, True])
+def test_two_force_objects_on_unordered_streams(mods, coracle, cooperative):
+    """Two CavityForceComputeGPU objects driven on two unordered streams (HOOMD itself uses one stream; this is the
+    shared-GPU situation).  With cooperative_launch every compute is correct.  With the default launches a grid that
+    was not co-resident is REPORTED -- the next compute of that object throws once, the object then launches
+    cooperatively -- and every compute after the report is correct; nothing hangs and no wrong force passes as good."""
+    from cav_hoomd_b200 import capi
+    shim, cav, _ = mods
+    s = synth.make_system(400000)
+    ref = coracle.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, 0.01, 1e-3)
+    scale = np.abs(ref["force"]).max()
+    objs, streams = [], [capi.Stream(), capi.Stream()]
+    for k in range(2):
+        sysdef, pd = make_sysdef(shim, s)
+        fc = cav.CavityForceComputeGPU(sysdef, 0.01, 1e-3)
+        fc.stream = streams[k].ptr
+        fc.cooperative_launch = cooperative
+        objs.append((fc, sysdef, pd))
+    thrown = 0
+    for t in range(10):
+        for fc, _, _ in objs:
+            try:
+                fc.compute(t)
+            except RuntimeError as e:
+                assert "cooperative" in str(e) and not cooperative
+                thrown += 1
+                assert fc.cooperative_launch and fc.getFaultCount() >= 1
+                fc.compute(t)  # redone, now co-scheduled by the driver
+        for fc, _, _ in objs:
+            try:
+                e_h = fc.getHarmonicEnergy()  # synchronises the object's stream
+            except RuntimeError:
+                assert not cooperative and not fc.cooperative_launch  # this very call timed out: reported, not wrong
+                continue
+            assert np.isclose(e_h, ref["energies"][0], rtol=1e-10)
+            f = fc.getForces()
+            assert np.abs(f - ref["force"]).max() <= 1e-10 * scale
+    if cooperative:
+        assert thrown == 0 and all(fc.getFaultCount() == 0 for fc, _, _ in objs)
+    capi.sync()
