@@ -6,7 +6,7 @@ NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall 
 CSRC      := cav_hoomd_b200/csrc
 LIBDIR    := cav_hoomd_b200/lib
 OBJDIR    := build/obj
-SRCS      := $(CSRC)/api.cu $(CSRC)/hotpath.cu $(CSRC)/rhok.cu $(CSRC)/shard.cu $(CSRC)/host.cu $(CSRC)/nve.cu $(CSRC)/track.cu
+SRCS      := $(CSRC)/api.cu $(CSRC)/hotpath.cu $(CSRC)/rhok.cu $(CSRC)/shard.cu $(CSRC)/host.cu $(CSRC)/nve.cu $(CSRC)/track.cu $(CSRC)/debug.cu
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 HDRS      := $(CSRC)/cavb200_internal.cuh $(CSRC)/hotpath.cuh include/cavb200.h
 

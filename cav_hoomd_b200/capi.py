@@ -57,6 +57,9 @@ _SIGNATURES = {
     "cavb200_launch_count": (_u64, [_vp]),
     "cavb200_fault_count": (_u64, [_vp]),
     "cavb200_debug_stamps": (C.c_int, [_vp, C.POINTER(C.c_uint64), _u32]),
+    "cavb200_debug_delay": (C.c_int, [_vp, _u64, _vp]),
+    "cavb200_debug_fp64_peak": (C.c_int, [_vp, _dp]),
+    "cavb200_debug_launch_ring": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint64), _u32, C.POINTER(C.c_uint64)]),
     "cavb200_set_tuning": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "cavb200_get_tuning": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int)]),
     "cavb200_force": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _vp]),
@@ -70,6 +73,14 @@ _SIGNATURES = {
     "cavb200_nve_half_kick": (C.c_int, [_vp, _vp, _vp, _u32, _dbl, _vp]),
     "cavb200_nvt_step_one": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _dbl, _u32, _u32, _BP, _vp]),
     "cavb200_nvt_step_two": (C.c_int, [_vp, _vp, _vp, _u32, _dbl, _u32, _u32, _vp]),
+    "cavb200_nve_kick_drift_wrap": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _dbl, _vp]),
+    "cavb200_nvt_step_one_wrap": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _dbl, _u32, _u32, _BP, _vp]),
+    "cavb200_nvt_step_one_rank1_wrap": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _dbl, _u32, _dbl,
+                                                  _u32, _u32, _BP, _vp]),
+    "cavb200_md_step_one_wrap": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _dbl, _u32, _PP, _u32, _u32,
+                                           _BP, _vp]),
+    "cavb200_md_step_fused_wrap": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _dbl, _u32, _PP, _u32,
+                                             _u32, _BP, _vp]),
     "cavb200_force_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _vp]),
     "cavb200_rank1_read": (C.c_int, [_vp, _dp, _dp, C.POINTER(C.c_int32), C.POINTER(_u32), _vp]),
     "cavb200_net_force_add_rank1": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _u32, _dbl, _vp]),
@@ -96,6 +107,9 @@ _SIGNATURES = {
     "cavb200_step_host_submit": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _u32, _u32,
                                            _BP]),
     "cavb200_step_host_wait": (C.c_int, [_vp, _u32, _dp, _dp]),
+    "cavb200_step_host_submit_ex": (C.c_int, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _u32,
+                                              _u32, _BP, _u32]),
+    "cavb200_step_host_wait_ex": (C.c_int, [_vp, _u32, _dp, _dp, _dp]),
     "cavb200_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _dbl, _dbl, _dbl, _u32, _PP, _u32, _u32, _BP,
                                     _dp, _dp]),
     "cavb200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
@@ -326,6 +340,23 @@ class Handle:
               "cavb200_debug_stamps")
         return out
 
+    def debug_delay(self, ns: int, stream=None):
+        check(self.lib.cavb200_debug_delay(self.h, int(ns), stream), "cavb200_debug_delay")
+
+    def debug_fp64_peak(self) -> float:
+        """FP64 fused multiply-adds per second of the device (DFMA microbenchmark)."""
+        v = C.c_double(0.0)
+        check(self.lib.cavb200_debug_fp64_peak(self.h, C.byref(v)), "cavb200_debug_fp64_peak")
+        return float(v.value)
+
+    def debug_launch_ring(self, reset: bool = False, read: bool = True):
+        """-> (ring uint64[2048, 2] of {start, end} ns, epoch of the last launch); tuning stamps = 2."""
+        out = np.zeros((2048, 2), dtype=np.uint64)
+        ep = C.c_uint64(0)
+        check(self.lib.cavb200_debug_launch_ring(self.h, int(reset), out.ctypes.data_as(C.POINTER(C.c_uint64)) if read else None,
+                                                 2048 if read else 0, C.byref(ep)), "cavb200_debug_launch_ring")
+        return out, int(ep.value)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.cavb200_launch_count(self.h))
@@ -383,6 +414,22 @@ class Handle:
                                                 C.byref(params), group_first, n_group, C.byref(bussi)),
               "cavb200_step_host_submit")
 
+    HOST_KEEP_CHARGE, HOST_KEEP_IMAGE, HOST_RANK1_RESULT = 1, 2, 4
+
+    def step_host_submit_ex(self, slot, pos, charge, image, force, vel, N, box, L_typeid, params, group_first, n_group,
+                            bussi, flags):
+        check(self.lib.cavb200_step_host_submit_ex(self.h, slot, _ptr(pos), _ptr(charge), _ptr(image), _ptr(force),
+                                                   _ptr(vel), N, box[0], box[1], box[2], L_typeid & 0xFFFFFFFF,
+                                                   C.byref(params), group_first, n_group, C.byref(bussi), flags),
+              "cavb200_step_host_submit_ex")
+
+    def step_host_wait_ex(self, slot):
+        """-> (energies[3], bussi dict, rank1 dict {Dq[2], F_L[3], photon_idx})"""
+        en, bo, r1 = (C.c_double * 3)(), (C.c_double * 5)(), (C.c_double * 6)()
+        check(self.lib.cavb200_step_host_wait_ex(self.h, slot, en, bo, r1), "cavb200_step_host_wait_ex")
+        return (np.array(en[:]), dict(ke=bo[0], alpha=bo[1], instantaneous=bo[2], cumulative=bo[3], err=bo[4]),
+                dict(Dq=np.array(r1[0:2]), F_L=np.array(r1[2:5]), photon_idx=int(r1[5])))
+
     def step_host_wait(self, slot):
         en = (C.c_double * 3)()
         bo = (C.c_double * 5)()
@@ -390,13 +437,24 @@ class Handle:
         return np.array(en[:]), dict(ke=bo[0], alpha=bo[1], instantaneous=bo[2], cumulative=bo[3], err=bo[4])
 
     # -- NVE harness ------------------------------------------------------------------------------
-    def nve_kick_drift(self, pos, vel, force, N, dt, stream=None):
+    def nve_kick_drift(self, pos, vel, force, N, dt, stream=None, image=None, box=None):
+        """image / box given: the drift is followed by the box wrap + image update (cavb200_nve_kick_drift_wrap)."""
+        if image is not None:
+            check(self.lib.cavb200_nve_kick_drift_wrap(self.h, _ptr(pos), _ptr(vel), _ptr(force), _ptr(image), N, dt,
+                                                       box[0], box[1], box[2], stream), "cavb200_nve_kick_drift_wrap")
+            return
         check(self.lib.cavb200_nve_kick_drift(self.h, _ptr(pos), _ptr(vel), _ptr(force), N, dt, stream),
               "cavb200_nve_kick_drift")
 
-    def nvt_step_one(self, pos, vel, force, N, dt, group_first, n_group, bussi=None, stream=None):
+    def nvt_step_one(self, pos, vel, force, N, dt, group_first, n_group, bussi=None, stream=None, image=None, box=None):
+        b = C.byref(bussi) if bussi is not None else None
+        if image is not None:
+            check(self.lib.cavb200_nvt_step_one_wrap(self.h, _ptr(pos), _ptr(vel), _ptr(force), _ptr(image), N, dt, box[0],
+                                                     box[1], box[2], group_first, n_group, b, stream),
+                  "cavb200_nvt_step_one_wrap")
+            return
         check(self.lib.cavb200_nvt_step_one(self.h, _ptr(pos), _ptr(vel), _ptr(force), N, dt, group_first, n_group,
-                                            C.byref(bussi) if bussi is not None else None, stream), "cavb200_nvt_step_one")
+                                            b, stream), "cavb200_nvt_step_one")
 
     def nvt_step_two(self, vel, force, N, dt, group_first, n_group, stream=None):
         check(self.lib.cavb200_nvt_step_two(self.h, _ptr(vel), _ptr(force), N, dt, group_first, n_group, stream),
@@ -419,22 +477,31 @@ class Handle:
               "cavb200_net_force_add_rank1")
 
     def nvt_step_one_rank1(self, pos, vel, force_other, charge, N, dt, L_typeid, couplstr, group_first, n_group,
-                           bussi=None, stream=None):
+                           bussi=None, stream=None, image=None, box=None):
+        if image is not None:
+            check(self.lib.cavb200_nvt_step_one_rank1_wrap(self.h, _ptr(pos), _ptr(vel), _ptr(force_other), _ptr(charge),
+                                                           _ptr(image), N, dt, box[0], box[1], box[2], L_typeid & 0xFFFFFFFF,
+                                                           couplstr, group_first, n_group,
+                                                           C.byref(bussi) if bussi is not None else None, stream),
+                  "cavb200_nvt_step_one_rank1_wrap")
+            return
         check(self.lib.cavb200_nvt_step_one_rank1(self.h, _ptr(pos), _ptr(vel), _ptr(force_other), _ptr(charge), N, dt,
                                                   L_typeid & 0xFFFFFFFF, couplstr, group_first, n_group,
                                                   C.byref(bussi) if bussi is not None else None, stream),
               "cavb200_nvt_step_one_rank1")
 
     def md_step_one(self, pos, vel, force_other, charge, image, N, dt, box, L_typeid, params, group_first, n_group,
-                    bussi=None, stream=None):
-        check(self.lib.cavb200_md_step_one(self.h, _ptr(pos), _ptr(vel), _ptr(force_other), _ptr(charge), _ptr(image), N,
+                    bussi=None, stream=None, wrap=False):
+        fn = self.lib.cavb200_md_step_one_wrap if wrap else self.lib.cavb200_md_step_one
+        check(fn(self.h, _ptr(pos), _ptr(vel), _ptr(force_other), _ptr(charge), _ptr(image), N,
                                            dt, box[0], box[1], box[2], L_typeid & 0xFFFFFFFF, C.byref(params), group_first,
                                            n_group, C.byref(bussi) if bussi is not None else None, stream),
               "cavb200_md_step_one")
 
     def md_step_fused(self, pos, vel, force_other, charge, image, N, dt, box, L_typeid, params, group_first, n_group,
-                      bussi=None, stream=None):
-        check(self.lib.cavb200_md_step_fused(self.h, _ptr(pos), _ptr(vel), _ptr(force_other), _ptr(charge), _ptr(image), N,
+                      bussi=None, stream=None, wrap=False):
+        fn = self.lib.cavb200_md_step_fused_wrap if wrap else self.lib.cavb200_md_step_fused
+        check(fn(self.h, _ptr(pos), _ptr(vel), _ptr(force_other), _ptr(charge), _ptr(image), N,
                                              dt, box[0], box[1], box[2], L_typeid & 0xFFFFFFFF, C.byref(params),
                                              group_first, n_group, C.byref(bussi) if bussi is not None else None, stream),
               "cavb200_md_step_fused")

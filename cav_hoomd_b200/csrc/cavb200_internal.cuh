@@ -21,6 +21,10 @@ constexpr uint32_t NO_INDEX = 0xFFFFFFFFu;
 constexpr unsigned long long HANDOFF_TIMEOUT_NS = 50000000ull; // 50 ms: a co-resident grid hands off in microseconds
 constexpr unsigned long long PEER_TIMEOUT_NS = 2000000000ull;  // 2 s: peer ranks may start late
 constexpr int MAX_PARTIALS = 2048; // upper bound on the grid of a reduce pass
+// stamps buffer (8 * MAX_PARTIALS u64): [0, 8192) per-CTA phase stamps, [8192, 12288) their second bank,
+// [12288, 16384) the per-launch ring of {start, end} pairs (tuning stamps = 2)
+constexpr unsigned long long LAUNCH_RING_OFFSET = 12288ull;
+constexpr unsigned long long LAUNCH_RING = 2048ull;
 
 // One reduce-pass record per CTA (and, in sharded mode, per rank): 160 bytes = five 32-byte sectors,
 // each written with ONE STG.256 and read with ONE LDG.256.  Every sector carries three payload words
@@ -85,7 +89,7 @@ struct Tuning
     int pdl;             // 1: launch with programmatic stream serialization (hides the launch gap; co-residency of the persistent
                          //    grids by construction on a device this stream has to itself); 0: cooperative launch (the driver
                          //    guarantees co-residency, ~2 us per launch slower).  Switched to 0 by the library after a fault.
-    int stamps;          // debug: record per-CTA phase timestamps of the cooperative kernel
+    int stamps;          // 1: debug, per-CTA phase timestamps of the persistent kernels; 2: per-launch {start, end} ring
     int md_shape;        // cavb200_md_step_fused launch shape: 0 = one 768-thread CTA per SM (default), 1 = two 384-thread CTAs
     int auto_threads;    // step kernel: pick 320 / 352 / 384 threads per CTA from the particle count (1) or use `threads` (0)
     int ke_first;        // folder step kernel: thermostat half first (1) or dipole half first (0)
@@ -128,6 +132,7 @@ struct cavb200_handle
     cudaEvent_t copy_events[64];
     int copy_ready;
     int slot_used[CAVB_HOST_SLOTS];
+    uint32_t slot_N[CAVB_HOST_SLOTS];  // particle count of the slot's last submit (KEEP_* flags)
     cavb::Scalars* slot_scalars;      // device, one per slot
     cavb::Scalars* slot_scalars_host; // pinned, one per slot
     // device-side tracker ring (track.cu): records | reference dipole | counter

@@ -13,7 +13,9 @@
 // The force of particle i needs the dipole of ALL particles, so within one step no force byte can
 // leave before the last position byte has arrived; the overlap comes from the velocity round trip and,
 // with two slots, from the next system's upload running under this system's download.
-// Per step PCIe carries 84 B/particle in and 64 B/particle out.
+// Per step PCIe carries 84 B/particle in and 64 B/particle out; cavb200_step_host_submit_ex lets the caller leave out
+// what has not changed since the slot's last submit (charges never change in an MD run, images rarely) and take the
+// rank-1 result {Dq, F_L, energies} instead of the 32 B/particle force array.
 #include "cavb200_internal.cuh"
 
 #include <math.h>
@@ -75,16 +77,22 @@ void cavb_host_release(cavb200_handle* h)
     h->copy_ready = 0;
     }
 
-extern "C" int cavb200_step_host_submit(cavb200_handle* h, uint32_t slot, const double* pos, const double* charge,
-                                        const int32_t* image, double* force, double* vel, uint32_t N, double Lx,
-                                        double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params,
-                                        uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi)
+extern "C" int cavb200_step_host_submit_ex(cavb200_handle* h, uint32_t slot, const double* pos, const double* charge,
+                                           const int32_t* image, double* force, double* vel, uint32_t N, double Lx,
+                                           double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params,
+                                           uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi,
+                                           uint32_t flags)
     {
     if (!h || !params || !bussi || slot >= CAVB_HOST_SLOTS)
         return (int)cudaErrorInvalidValue;
     if (N == 0)
         return 0;
-    if (!pos || !charge || !image || !force || !vel)
+    const bool keep_charge = (flags & CAVB200_HOST_KEEP_CHARGE) != 0, keep_image = (flags & CAVB200_HOST_KEEP_IMAGE) != 0;
+    const bool rank1 = (flags & CAVB200_HOST_RANK1_RESULT) != 0;
+    if (!pos || (!charge && !keep_charge) || (!image && !keep_image) || (!force && !rank1) || !vel)
+        return (int)cudaErrorInvalidValue;
+    // "unchanged since the last submit on this slot": the slot's device copy must exist and be of this size
+    if ((keep_charge || keep_image) && (!h->slot_used[slot] || h->slot_N[slot] != N))
         return (int)cudaErrorInvalidValue;
     if ((unsigned long long)group_first + n_group > N)
         return (int)cudaErrorInvalidValue;
@@ -113,8 +121,10 @@ extern "C" int cavb200_step_host_submit(cavb200_handle* h, uint32_t slot, const 
         CAVB_CHECK(cudaMemcpyAsync(d_vel + voff, vel + voff, 32ull * n_group, cudaMemcpyHostToDevice, sIn));
     CAVB_CHECK(cudaEventRecord(ev[EV_VEL_IN], sIn));
     CAVB_CHECK(cudaMemcpyAsync(d_pos, pos, 32 * n, cudaMemcpyHostToDevice, sIn));
-    CAVB_CHECK(cudaMemcpyAsync(d_charge, charge, 8 * n, cudaMemcpyHostToDevice, sIn));
-    CAVB_CHECK(cudaMemcpyAsync(d_image, image, 12 * n, cudaMemcpyHostToDevice, sIn));
+    if (!keep_charge)
+        CAVB_CHECK(cudaMemcpyAsync(d_charge, charge, 8 * n, cudaMemcpyHostToDevice, sIn));
+    if (!keep_image)
+        CAVB_CHECK(cudaMemcpyAsync(d_image, image, 12 * n, cudaMemcpyHostToDevice, sIn));
     CAVB_CHECK(cudaEventRecord(ev[EV_POS_IN], sIn));
     // kernels, one stream
     CAVB_CHECK(cudaStreamWaitEvent(sK, ev[EV_VEL_IN], 0));
@@ -126,7 +136,10 @@ extern "C" int cavb200_step_host_submit(cavb200_handle* h, uint32_t slot, const 
         }
     CAVB_CHECK(cudaEventRecord(ev[EV_BUSSI_DONE], sK));
     CAVB_CHECK(cudaStreamWaitEvent(sK, ev[EV_POS_IN], 0));
-    rc = cavb200_force(h, d_pos, d_charge, d_image, d_force, N, Lx, Ly, Lz, L_typeid, params, sK);
+    // rank-1 result: the dipole reduce alone (nothing written per particle); the caller forms
+    // F_i = (-g c_i) Dq from the charges it already holds (reference src/CavityForceCompute.cc:188-200)
+    rc = rank1 ? cavb200_force_rank1(h, d_pos, d_charge, d_image, N, Lx, Ly, Lz, L_typeid, params, sK)
+               : cavb200_force(h, d_pos, d_charge, d_image, d_force, N, Lx, Ly, Lz, L_typeid, params, sK);
     if (rc)
         return rc;
     // the Scalars block is per handle: keep this step's copy before the next submit's kernels run
@@ -137,11 +150,41 @@ extern "C" int cavb200_step_host_submit(cavb200_handle* h, uint32_t slot, const 
     if (thermostat)
         CAVB_CHECK(cudaMemcpyAsync(vel + voff, d_vel + voff, 32ull * n_group, cudaMemcpyDeviceToHost, sOut));
     CAVB_CHECK(cudaStreamWaitEvent(sOut, ev[EV_FORCE_DONE], 0));
-    CAVB_CHECK(cudaMemcpyAsync(force, d_force, 32 * n, cudaMemcpyDeviceToHost, sOut));
+    if (!rank1)
+        CAVB_CHECK(cudaMemcpyAsync(force, d_force, 32 * n, cudaMemcpyDeviceToHost, sOut));
     CAVB_CHECK(cudaMemcpyAsync(h->slot_scalars_host + slot, h->slot_scalars + slot, sizeof(Scalars),
                                cudaMemcpyDeviceToHost, sOut));
     CAVB_CHECK(cudaEventRecord(ev[EV_DONE], sOut));
     h->slot_used[slot] = 1;
+    h->slot_N[slot] = N;
+    return 0;
+    }
+
+extern "C" int cavb200_step_host_submit(cavb200_handle* h, uint32_t slot, const double* pos, const double* charge,
+                                        const int32_t* image, double* force, double* vel, uint32_t N, double Lx,
+                                        double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params,
+                                        uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi)
+    {
+    return cavb200_step_host_submit_ex(h, slot, pos, charge, image, force, vel, N, Lx, Ly, Lz, L_typeid, params, group_first,
+                                       n_group, bussi, 0u);
+    }
+
+extern "C" int cavb200_step_host_wait_ex(cavb200_handle* h, uint32_t slot, double energies[3], double bussi_out[5],
+                                         double rank1_out[6])
+    {
+    const int rc = cavb200_step_host_wait(h, slot, energies, bussi_out);
+    if (rc)
+        return rc;
+    if (rank1_out)
+        {
+        const Scalars& s = h->slot_scalars_host[slot];
+        rank1_out[0] = s.Dq[0];
+        rank1_out[1] = s.Dq[1];
+        rank1_out[2] = s.FL[0];
+        rank1_out[3] = s.FL[1];
+        rank1_out[4] = s.FL[2];
+        rank1_out[5] = (double)s.photon_idx;
+        }
     return 0;
     }
 

@@ -17,6 +17,20 @@
 
 namespace cavb
     {
+// Per-launch device timestamps (tuning "stamps" = 2; bench.py's kernel_ms_device): the upper quarter of the stamps
+// buffer is a ring of LAUNCH_RING {first CTA start, last CTA end} pairs in globaltimer ns, indexed by the launch's
+// epoch; every CTA contributes one atomicMin and one atomicMax.  cavb200_debug_launch_ring resets / reads it.
+__device__ __forceinline__ void ring_stamp(unsigned long long* stamps, int mode, unsigned long long epoch,
+                                           unsigned long long t_start)
+    {
+    if (mode == 2 && threadIdx.x == 0)
+        {
+        unsigned long long* r = stamps + LAUNCH_RING_OFFSET + 2ull * (epoch & (LAUNCH_RING - 1));
+        atomicMin(r, t_start);
+        atomicMax(r + 1, globaltimer_ns());
+        }
+    }
+
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
@@ -71,11 +85,12 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1) k_apply(ForceIn f, Buss
 template<bool FORCE, bool BUSSI, int UNROLL, int LB>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_fused(ForceIn f, BussiIn b, Partial* recs, Scalars* scalars, unsigned long long* epoch_ctr,
-            unsigned long long* stamps)
+            unsigned long long* stamps, int stamp_mode)
     {
     __shared__ BlockScratch sc;
     // optional phase stamps (tools/phase_stamps.py): thread 0 of every CTA, globaltimer ns
-    unsigned long long* my_stamps = (stamps && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
+    unsigned long long* my_stamps = (stamp_mode == 1 && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
+    const unsigned long long t_start = stamp_mode == 2 ? globaltimer_ns() : 0ull;
     if (my_stamps)
         my_stamps[0] = globaltimer_ns();
     // programmatic dependent launch: this grid may have been scheduled while the previous kernel of
@@ -129,6 +144,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         apply_phase<FORCE, BUSSI, UNROLL>(sc.fin, f, b);
     if (my_stamps)
         my_stamps[4] = globaltimer_ns();
+    ring_stamp(stamps, stamp_mode, epoch, t_start);
     }
 
 // variant 2 ("split-phase"): the thermostat half and the force half are independent, so their two
@@ -141,10 +157,11 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
 template<int UNROLL, int LB>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_split(ForceIn f, BussiIn b, Partial* recsF, Partial* recsB, Scalars* scalars, unsigned long long* epoch_ctr,
-            unsigned long long* stamps)
+            unsigned long long* stamps, int stamp_mode)
     {
     __shared__ BlockScratch sc;
-    unsigned long long* my_stamps = (stamps && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
+    unsigned long long* my_stamps = (stamp_mode == 1 && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
+    const unsigned long long t_start = stamp_mode == 2 ? globaltimer_ns() : 0ull;
     if (my_stamps)
         my_stamps[0] = globaltimer_ns();
     pdl_wait();
@@ -192,6 +209,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     apply_phase<false, true, UNROLL>(sc.fin, f, b);
     if (my_stamps)
         my_stamps[6] = globaltimer_ns();
+    ring_stamp(stamps, stamp_mode, epoch, t_start);
     }
 
 // variant 3 ("split-phase with a folder CTA"): the split-phase schedule, but ONE extra CTA that streams
@@ -205,10 +223,11 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
 template<int UNROLL, int LB, bool KE_FIRST>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_split_folder(ForceIn f, BussiIn b, Partial* recsF, Partial* recsB, Partial* finals, Scalars* scalars,
-                   unsigned long long* epoch_ctr, unsigned long long* stamps)
+                   unsigned long long* epoch_ctr, unsigned long long* stamps, int stamp_mode)
     {
     __shared__ BlockScratch sc;
-    unsigned long long* my_stamps = (stamps && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
+    unsigned long long* my_stamps = (stamp_mode == 1 && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
+    const unsigned long long t_start = stamp_mode == 2 ? globaltimer_ns() : 0ull;
     if (my_stamps)
         my_stamps[0] = globaltimer_ns();
     pdl_wait();
@@ -286,6 +305,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
                 *epoch_ctr = epoch; // every streaming CTA has published twice, hence read the counter
             }
         pdl_launch_dependents();
+        ring_stamp(stamps, stamp_mode, epoch, t_start);
         return;
         }
     // ---- streaming CTAs ----
@@ -376,6 +396,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         }
     if (my_stamps)
         my_stamps[6] = globaltimer_ns();
+    ring_stamp(stamps, stamp_mode, epoch, t_start);
     }
 
 // ------------------------------------------------------------------------------------------
@@ -451,9 +472,10 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         unsigned long long* arr = h->counters + 2;
         ForceIn ff = f;
         BussiIn bb = b;
-        unsigned long long* stamps = h->tune.stamps ? h->stamps : nullptr;
-        void* args_split[] = {&ff, &bb, &recsF, &recsB, &sca, &arr, &stamps};
-        void* args_folder[] = {&ff, &bb, &recsF, &recsB, &finals, &sca, &arr, &stamps};
+        unsigned long long* stamps = h->stamps;
+        int stamp_mode = h->tune.stamps;
+        void* args_split[] = {&ff, &bb, &recsF, &recsB, &sca, &arr, &stamps, &stamp_mode};
+        void* args_folder[] = {&ff, &bb, &recsF, &recsB, &finals, &sca, &arr, &stamps, &stamp_mode};
         void** args = folder ? args_folder : args_split;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
@@ -522,8 +544,9 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         unsigned long long* arr = h->counters + 2;
         ForceIn ff = f;
         BussiIn bb = b;
-        unsigned long long* stamps = h->tune.stamps ? h->stamps : nullptr;
-        void* args[] = {&ff, &bb, &recs, &sca, &arr, &stamps};
+        unsigned long long* stamps = h->stamps;
+        int stamp_mode = h->tune.stamps;
+        void* args[] = {&ff, &bb, &recs, &sca, &arr, &stamps, &stamp_mode};
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(threads);

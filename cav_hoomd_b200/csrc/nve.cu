@@ -29,6 +29,44 @@ struct Rank1In
     ForceIn f; // pos (type look-up, only when several 'L' particles exist), L_typeid, g
     };
 
+// Box wrap of the drift (r <- r + v dt, wrap): HOOMD's BoxDim::wrap for an orthorhombic box that is
+// periodic in all three directions, [-L/2, L/2) -- one shift per direction, the image flag follows
+// [HOOMD-upstream, not in the reference tree: restated from its definition; oracle: orc_wrap].
+__device__ __forceinline__ bool wrap_one(double& x, int& img, double L, double hi)
+    {
+    if (x >= hi)
+        {
+        x = __dadd_rn(x, -L);
+        img++;
+        return true;
+        }
+    if (x < -hi)
+        {
+        x = __dadd_rn(x, L);
+        img--;
+        return true;
+        }
+    return false;
+    }
+struct WrapIn
+    {
+    int* image; // int3 per particle, read and (when a particle crosses a face) written
+    double Lx, Ly, Lz;
+    };
+// wrap p and keep the particle's image flags in step; returns the (new) flags
+__device__ __forceinline__ void wrap_particle(double4& p, unsigned long long i, const WrapIn& w, int& ix, int& iy, int& iz)
+    {
+    bool ch = wrap_one(p.x, ix, w.Lx, __dmul_rn(0.5, w.Lx));
+    ch = wrap_one(p.y, iy, w.Ly, __dmul_rn(0.5, w.Ly)) || ch;
+    ch = wrap_one(p.z, iz, w.Lz, __dmul_rn(0.5, w.Lz)) || ch;
+    if (ch)
+        {
+        w.image[3 * i + 0] = ix;
+        w.image[3 * i + 1] = iy;
+        w.image[3 * i + 2] = iz;
+        }
+    }
+
 template<bool RANK1>
 __device__ __forceinline__ double4 kick_force(const double4* force, unsigned long long i, const Rank1In& r, const Final& fin)
     {
@@ -46,10 +84,10 @@ __device__ __forceinline__ double4 kick_force(const double4* force, unsigned lon
     return fc;
     }
 
-template<bool RANK1>
+template<bool RANK1, bool WRAP>
 __global__ void __launch_bounds__(256)
     k_nvt_one(double4* pos, double4* vel, const double4* force, uint32_t N, double dt, BussiIn b, Scalars* scalars,
-              Rank1In r1)
+              Rank1In r1, WrapIn w)
     {
     __shared__ double s_alpha;
     __shared__ Final s_fin;
@@ -100,6 +138,11 @@ __global__ void __launch_bounds__(256)
         p.x = __dadd_rn(p.x, __dmul_rn(dt, v.x));
         p.y = __dadd_rn(p.y, __dmul_rn(dt, v.y));
         p.z = __dadd_rn(p.z, __dmul_rn(dt, v.z));
+        if (WRAP)
+            {
+            int ix = w.image[3 * i + 0], iy = w.image[3 * i + 1], iz = w.image[3 * i + 2];
+            wrap_particle(p, i, w, ix, iy, iz);
+            }
         st256(vel + i, v);
         st256(pos + i, p);
         }
@@ -164,9 +207,10 @@ __global__ void __launch_bounds__(256)
 // (src/CavityForceCompute.cc:107-109,124) -- positions are never read a second time.  The last CTA to take a
 // ticket folds the CTA records and leaves the new Scalars / Final for step two.  One launch replaces
 // cavb200_nvt_step_one_rank1 + cavb200_force_rank1.
+template<bool WRAP>
 __global__ void __launch_bounds__(256, 3)
     k_md_one(double4* pos, double4* vel, const double4* force_other, uint32_t N, double dt, BussiIn b, Scalars* scalars,
-             Rank1In r1, ForceIn fnew, Partial* recs, unsigned long long* ticket, Final* fin_out)
+             Rank1In r1, ForceIn fnew, Partial* recs, unsigned long long* ticket, Final* fin_out, WrapIn w)
     {
     __shared__ BlockScratch sc;
     __shared__ double s_alpha;
@@ -207,7 +251,10 @@ __global__ void __launch_bounds__(256, 3)
         double4 v = ld256(vel + i);
         double4 p = ld256(pos + i);
         const double c = __ldg(fnew.charge + i);
-        const int ix = __ldg(fnew.image + 3 * i + 0), iy = __ldg(fnew.image + 3 * i + 1), iz = __ldg(fnew.image + 3 * i + 2);
+        // (WRAP: this kernel rewrites the image flags, so they are read coherently, not through the read-only path)
+        int ix = WRAP ? w.image[3 * i + 0] : __ldg(fnew.image + 3 * i + 0);
+        int iy = WRAP ? w.image[3 * i + 1] : __ldg(fnew.image + 3 * i + 1);
+        int iz = WRAP ? w.image[3 * i + 2] : __ldg(fnew.image + 3 * i + 2);
         double4 f = force_of(i, c, s_fin, r1.f);
         if (force_other)
             {
@@ -229,6 +276,8 @@ __global__ void __launch_bounds__(256, 3)
         p.x = __dadd_rn(p.x, __dmul_rn(dt, v.x));
         p.y = __dadd_rn(p.y, __dmul_rn(dt, v.y));
         p.z = __dadd_rn(p.z, __dmul_rn(dt, v.z));
+        if (WRAP)
+            wrap_particle(p, i, w, ix, iy, iz);
         st256(vel + i, v);
         st256(pos + i, p);
         take_particle(a, (unsigned int)i, p, c, ix, iy, iz, fnew);
@@ -263,11 +312,11 @@ __global__ void __launch_bounds__(256, 3)
 // pass, an L2 hit at 1M particles).  Structure of k_split_folder: 295 streaming CTAs, one folder CTA.
 //     streaming CTA:  pass 1 (v1 on the fly, KE) -> publish | take alpha | pass 2 (v2, r, dipole) -> publish
 //     folder CTA:     fold KE records -> alpha -> Final(K) | fold dipole records -> Scalars, Final for the next step
-template<int LB, int U2>
+template<int LB, int U2, bool WRAP>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_md_fused(double4* pos, double4* vel, const double4* force_other, uint32_t N, double dt, BussiIn b, Rank1In r1,
                ForceIn fnew, Partial* recsF, Partial* recsB, Partial* finals, Scalars* scalars,
-               unsigned long long* epoch_ctr, Final* fin_out)
+               unsigned long long* epoch_ctr, Final* fin_out, WrapIn w)
     {
     __shared__ BlockScratch sc;
     __shared__ Final s_fin;
@@ -406,6 +455,8 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         p.x = __dadd_rn(p.x, __dmul_rn(dt, v.x));
         p.y = __dadd_rn(p.y, __dmul_rn(dt, v.y));
         p.z = __dadd_rn(p.z, __dmul_rn(dt, v.z));
+        if (WRAP)
+            wrap_particle(p, i, w, ix, iy, iz);
         st256(vel + i, v);
         st256(pos + i, p);
         take_particle(a, (unsigned int)i, p, c, ix, iy, iz, fnew);
@@ -423,9 +474,9 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
             v[k] = ld256(vel + j);
             p[k] = ld256_na(pos + j); // coherent: this kernel overwrites pos (no .nc)
             c[k] = __ldg(r1.charge + j);
-            ix[k] = __ldg(fnew.image + 3 * j + 0);
-            iy[k] = __ldg(fnew.image + 3 * j + 1);
-            iz[k] = __ldg(fnew.image + 3 * j + 2);
+            ix[k] = WRAP ? w.image[3 * j + 0] : __ldg(fnew.image + 3 * j + 0);
+            iy[k] = WRAP ? w.image[3 * j + 1] : __ldg(fnew.image + 3 * j + 1);
+            iz[k] = WRAP ? w.image[3 * j + 2] : __ldg(fnew.image + 3 * j + 2);
             if (force_other)
                 f[k] = ld256(force_other + j);
             }
@@ -454,8 +505,9 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
             fc.y = __dadd_rn(fo.y, fc.y);
             fc.z = __dadd_rn(fo.z, fc.z);
             }
-        finish(i, ld256(vel + i), ld256_na(pos + i), c, __ldg(fnew.image + 3 * i + 0), __ldg(fnew.image + 3 * i + 1),
-               __ldg(fnew.image + 3 * i + 2), fc);
+        finish(i, ld256(vel + i), ld256_na(pos + i), c, WRAP ? w.image[3 * i + 0] : __ldg(fnew.image + 3 * i + 0),
+               WRAP ? w.image[3 * i + 1] : __ldg(fnew.image + 3 * i + 1),
+               WRAP ? w.image[3 * i + 2] : __ldg(fnew.image + 3 * i + 2), fc);
         }
     block_merge<true, false>(a, fnew, sc);
     if (threadIdx.x == 0)
@@ -463,8 +515,8 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     pdl_launch_dependents();
     }
 
-template<bool DRIFT>
-__global__ void __launch_bounds__(256) k_nve(double4* pos, double4* vel, const double4* force, uint32_t N, double dt)
+template<bool DRIFT, bool WRAP>
+__global__ void __launch_bounds__(256) k_nve(double4* pos, double4* vel, const double4* force, uint32_t N, double dt, WrapIn w)
     {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
@@ -482,6 +534,11 @@ __global__ void __launch_bounds__(256) k_nve(double4* pos, double4* vel, const d
             p.x = __dadd_rn(p.x, __dmul_rn(dt, v.x));
             p.y = __dadd_rn(p.y, __dmul_rn(dt, v.y));
             p.z = __dadd_rn(p.z, __dmul_rn(dt, v.z));
+            if (WRAP)
+                {
+                int ix = w.image[3 * i + 0], iy = w.image[3 * i + 1], iz = w.image[3 * i + 2];
+                wrap_particle(p, i, w, ix, iy, iz);
+                }
             st256(pos + i, p);
             }
         }
@@ -490,8 +547,21 @@ __global__ void __launch_bounds__(256) k_nve(double4* pos, double4* vel, const d
 
 using namespace cavb;
 
+static int make_wrap(WrapIn& w, int32_t* image, double Lx, double Ly, double Lz)
+    {
+    if (!image || !(Lx > 0.0) || !(Ly > 0.0) || !(Lz > 0.0))
+        return (int)cudaErrorInvalidValue;
+    if (reinterpret_cast<uintptr_t>(image) & 3)
+        return (int)cudaErrorMisalignedAddress;
+    w.image = image;
+    w.Lx = Lx;
+    w.Ly = Ly;
+    w.Lz = Lz;
+    return 0;
+    }
+
 static int nve_launch(cavb200_handle* h, double* pos, double* vel, const double* force, uint32_t N, double dt,
-                      cudaStream_t s, bool drift)
+                      cudaStream_t s, bool drift, const WrapIn* w = nullptr)
     {
     if (!h)
         return (int)cudaErrorInvalidValue;
@@ -504,10 +574,12 @@ static int nve_launch(cavb200_handle* h, double* pos, double* vel, const double*
     unsigned long long want = ((unsigned long long)N + 255) / 256;
     const unsigned long long cap = (unsigned long long)h->num_sms * 8;
     const int grid = (int)(want < cap ? want : cap);
-    if (drift)
-        k_nve<true><<<grid, 256, 0, s>>>((double4*)pos, (double4*)vel, (const double4*)force, N, dt);
+    if (drift && w)
+        k_nve<true, true><<<grid, 256, 0, s>>>((double4*)pos, (double4*)vel, (const double4*)force, N, dt, *w);
+    else if (drift)
+        k_nve<true, false><<<grid, 256, 0, s>>>((double4*)pos, (double4*)vel, (const double4*)force, N, dt, WrapIn());
     else
-        k_nve<false><<<grid, 256, 0, s>>>(nullptr, (double4*)vel, (const double4*)force, N, dt);
+        k_nve<false, false><<<grid, 256, 0, s>>>(nullptr, (double4*)vel, (const double4*)force, N, dt, WrapIn());
     CAVB_CHECK(cudaGetLastError());
     h->launches += 1;
     return 0;
@@ -517,6 +589,15 @@ extern "C" int cavb200_nve_kick_drift(cavb200_handle* h, double* pos, double* ve
                                       double dt, void* stream)
     {
     return nve_launch(h, pos, vel, force, N, dt, (cudaStream_t)stream, true);
+    }
+
+extern "C" int cavb200_nve_kick_drift_wrap(cavb200_handle* h, double* pos, double* vel, const double* force, int32_t* image,
+                                           uint32_t N, double dt, double Lx, double Ly, double Lz, void* stream)
+    {
+    WrapIn w;
+    if (const int rc = make_wrap(w, image, Lx, Ly, Lz))
+        return rc;
+    return nve_launch(h, pos, vel, force, N, dt, (cudaStream_t)stream, true, &w);
     }
 
 extern "C" int cavb200_nve_half_kick(cavb200_handle* h, double* vel, const double* force, uint32_t N, double dt,
@@ -557,7 +638,8 @@ static int fill_rank1(cavb200_handle* h, Rank1In& r, const double* charge, const
     }
 
 static int nvt_one(cavb200_handle* h, double* pos, double* vel, const double* force, uint32_t N, double dt,
-                   uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, const Rank1In* r1, void* stream)
+                   uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, const Rank1In* r1, void* stream,
+                   const WrapIn* w = nullptr)
     {
     if (!pos || !vel || (!force && !r1) || (unsigned long long)group_first + n_group > N)
         return (int)cudaErrorInvalidValue;
@@ -572,12 +654,17 @@ static int nvt_one(cavb200_handle* h, double* pos, double* vel, const double* fo
     unsigned long long want = ((unsigned long long)N + 255) / 256;
     const unsigned long long cap = (unsigned long long)h->num_sms * CAVB_NVT_CTAS_PER_SM;
     const int grid = (int)(want < cap ? want : cap);
-    if (r1)
-        k_nvt_one<true><<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)pos, (double4*)vel, (const double4*)force, N, dt,
-                                                                b, h->scalars, *r1);
+    cudaStream_t cs = (cudaStream_t)stream;
+    double4 *p4 = (double4*)pos, *v4 = (double4*)vel;
+    const double4* f4 = (const double4*)force;
+    if (r1 && w)
+        k_nvt_one<true, true><<<grid, 256, 0, cs>>>(p4, v4, f4, N, dt, b, h->scalars, *r1, *w);
+    else if (r1)
+        k_nvt_one<true, false><<<grid, 256, 0, cs>>>(p4, v4, f4, N, dt, b, h->scalars, *r1, WrapIn());
+    else if (w)
+        k_nvt_one<false, true><<<grid, 256, 0, cs>>>(p4, v4, f4, N, dt, b, h->scalars, Rank1In(), *w);
     else
-        k_nvt_one<false><<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)pos, (double4*)vel, (const double4*)force, N,
-                                                                 dt, b, h->scalars, Rank1In());
+        k_nvt_one<false, false><<<grid, 256, 0, cs>>>(p4, v4, f4, N, dt, b, h->scalars, Rank1In(), WrapIn());
     CAVB_CHECK(cudaGetLastError());
     h->launches += 1;
     return 0;
@@ -619,6 +706,20 @@ extern "C" int cavb200_nvt_step_one(cavb200_handle* h, double* pos, double* vel,
     return nvt_one(h, pos, vel, force, N, dt, group_first, n_group, bussi, nullptr, stream);
     }
 
+extern "C" int cavb200_nvt_step_one_wrap(cavb200_handle* h, double* pos, double* vel, const double* force, int32_t* image,
+                                         uint32_t N, double dt, double Lx, double Ly, double Lz, uint32_t group_first,
+                                         uint32_t n_group, const cavb200_bussi_args* bussi, void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    WrapIn w;
+    if (const int rc = make_wrap(w, image, Lx, Ly, Lz))
+        return rc;
+    return nvt_one(h, pos, vel, force, N, dt, group_first, n_group, bussi, nullptr, stream, &w);
+    }
+
 extern "C" int cavb200_nvt_step_two(cavb200_handle* h, double* vel, const double* force, uint32_t N, double dt,
                                     uint32_t group_first, uint32_t n_group, void* stream)
     {
@@ -645,6 +746,25 @@ extern "C" int cavb200_nvt_step_one_rank1(cavb200_handle* h, double* pos, double
     return nvt_one(h, pos, vel, force_other, N, dt, group_first, n_group, bussi, &r, stream);
     }
 
+extern "C" int cavb200_nvt_step_one_rank1_wrap(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                                               const double* charge, int32_t* image, uint32_t N, double dt, double Lx,
+                                               double Ly, double Lz, uint32_t L_typeid, double couplstr,
+                                               uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi,
+                                               void* stream)
+    {
+    if (!h)
+        return (int)cudaErrorInvalidValue;
+    if (N == 0)
+        return 0;
+    Rank1In r;
+    if (const int rc = fill_rank1(h, r, charge, pos, L_typeid, couplstr))
+        return rc;
+    WrapIn w;
+    if (const int rc = make_wrap(w, image, Lx, Ly, Lz))
+        return rc;
+    return nvt_one(h, pos, vel, force_other, N, dt, group_first, n_group, bussi, &r, stream, &w);
+    }
+
 extern "C" int cavb200_nvt_step_two_rank1(cavb200_handle* h, double* vel, const double* force_other, const double* charge,
                                           const double* pos, uint32_t N, double dt, uint32_t L_typeid, double couplstr,
                                           uint32_t group_first, uint32_t n_group, void* stream)
@@ -660,10 +780,10 @@ extern "C" int cavb200_nvt_step_two_rank1(cavb200_handle* h, double* vel, const 
     return nvt_two(h, vel, force_other, N, dt, group_first, n_group, &r, stream);
     }
 
-extern "C" int cavb200_md_step_one(cavb200_handle* h, double* pos, double* vel, const double* force_other,
-                                   const double* charge, const int32_t* image, uint32_t N, double dt, double Lx, double Ly,
-                                   double Lz, uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
-                                   uint32_t n_group, const cavb200_bussi_args* bussi, void* stream)
+static int md_step_one_impl(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                            const double* charge, const int32_t* image, uint32_t N, double dt, double Lx, double Ly,
+                            double Lz, uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
+                            uint32_t n_group, const cavb200_bussi_args* bussi, void* stream, bool wrap)
     {
     if (!h)
         return (int)cudaErrorInvalidValue;
@@ -700,18 +820,46 @@ extern "C" int cavb200_md_step_one(cavb200_handle* h, double* pos, double* vel, 
     if (cap > (unsigned long long)MAX_PARTIALS)
         cap = MAX_PARTIALS;
     const int grid = (int)(want < cap ? want : cap);
-    k_md_one<<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)pos, (double4*)vel, (const double4*)force_other, N, dt, b,
-                                                      h->scalars, r, fnew, h->partials, h->counters + 4,
-                                                      const_cast<Final*>(rank1_final(h)));
+    WrapIn w = WrapIn();
+    if (wrap)
+        {
+        if (const int rcw = make_wrap(w, const_cast<int32_t*>(image), Lx, Ly, Lz))
+            return rcw;
+        k_md_one<true><<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)pos, (double4*)vel, (const double4*)force_other, N,
+                                                                dt, b, h->scalars, r, fnew, h->partials, h->counters + 4,
+                                                                const_cast<Final*>(rank1_final(h)), w);
+        }
+    else
+        k_md_one<false><<<grid, 256, 0, (cudaStream_t)stream>>>((double4*)pos, (double4*)vel, (const double4*)force_other, N,
+                                                                 dt, b, h->scalars, r, fnew, h->partials, h->counters + 4,
+                                                                 const_cast<Final*>(rank1_final(h)), w);
     CAVB_CHECK(cudaGetLastError());
     h->launches += 1;
     return 0;
     }
 
-extern "C" int cavb200_md_step_fused(cavb200_handle* h, double* pos, double* vel, const double* force_other,
-                                     const double* charge, const int32_t* image, uint32_t N, double dt, double Lx,
-                                     double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params,
-                                     uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, void* stream)
+extern "C" int cavb200_md_step_one(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                                   const double* charge, const int32_t* image, uint32_t N, double dt, double Lx, double Ly,
+                                   double Lz, uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
+                                   uint32_t n_group, const cavb200_bussi_args* bussi, void* stream)
+    {
+    return md_step_one_impl(h, pos, vel, force_other, charge, image, N, dt, Lx, Ly, Lz, L_typeid, params, group_first, n_group,
+                            bussi, stream, false);
+    }
+
+extern "C" int cavb200_md_step_one_wrap(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                                        const double* charge, int32_t* image, uint32_t N, double dt, double Lx, double Ly,
+                                        double Lz, uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
+                                        uint32_t n_group, const cavb200_bussi_args* bussi, void* stream)
+    {
+    return md_step_one_impl(h, pos, vel, force_other, charge, image, N, dt, Lx, Ly, Lz, L_typeid, params, group_first, n_group,
+                            bussi, stream, true);
+    }
+
+static int md_step_fused_impl(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                              const double* charge, const int32_t* image, uint32_t N, double dt, double Lx,
+                              double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params,
+                              uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, void* stream, bool wrap)
     {
     if (!h)
         return (int)cudaErrorInvalidValue;
@@ -749,10 +897,22 @@ extern "C" int cavb200_md_step_fused(cavb200_handle* h, double* pos, double* vel
         fill_bussi_constants(b, bussi);
     const void* kern;
     int threads, per_sm_want;
+    WrapIn w = WrapIn();
+    if (wrap)
+        if (const int rcw = make_wrap(w, const_cast<int32_t*>(image), Lx, Ly, Lz))
+            return rcw;
     switch (h->tune.md_shape)
         {
-    case 1:  kern = (const void*)k_md_fused<384, 1>; threads = 384; per_sm_want = 2; break;
-    default: kern = (const void*)k_md_fused<768, 1>; threads = 768; per_sm_want = 1; break; // folder CTA alone on its SM
+    case 1:
+        kern = wrap ? (const void*)k_md_fused<384, 1, true> : (const void*)k_md_fused<384, 1, false>;
+        threads = 384;
+        per_sm_want = 2;
+        break;
+    default: // folder CTA alone on its SM
+        kern = wrap ? (const void*)k_md_fused<768, 1, true> : (const void*)k_md_fused<768, 1, false>;
+        threads = 768;
+        per_sm_want = 1;
+        break;
         }
     int per_sm = 0;
     CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
@@ -775,7 +935,7 @@ extern "C" int cavb200_md_step_fused(cavb200_handle* h, double* pos, double* vel
     Scalars* sca = h->scalars;
     unsigned long long* ctr = h->counters + 2;
     Final* fin_out = const_cast<Final*>(rank1_final(h));
-    void* args[] = {&p4, &v4, &fo4, &N, &dt, &b, &r, &fnew, &recsF, &recsB, &finals, &sca, &ctr, &fin_out};
+    void* args[] = {&p4, &v4, &fo4, &N, &dt, &b, &r, &fnew, &recsF, &recsB, &finals, &sca, &ctr, &fin_out, &w};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(threads);
@@ -796,6 +956,25 @@ extern "C" int cavb200_md_step_fused(cavb200_handle* h, double* pos, double* vel
     CAVB_CHECK(cudaLaunchKernelExC(&cfg, kern, args));
     h->launches += 1;
     return 0;
+    }
+
+extern "C" int cavb200_md_step_fused(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                                     const double* charge, const int32_t* image, uint32_t N, double dt, double Lx,
+                                     double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params,
+                                     uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi, void* stream)
+    {
+    return md_step_fused_impl(h, pos, vel, force_other, charge, image, N, dt, Lx, Ly, Lz, L_typeid, params, group_first,
+                              n_group, bussi, stream, false);
+    }
+
+extern "C" int cavb200_md_step_fused_wrap(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                                          const double* charge, int32_t* image, uint32_t N, double dt, double Lx,
+                                          double Ly, double Lz, uint32_t L_typeid, const cavb200_params* params,
+                                          uint32_t group_first, uint32_t n_group, const cavb200_bussi_args* bussi,
+                                          void* stream)
+    {
+    return md_step_fused_impl(h, pos, vel, force_other, charge, image, N, dt, Lx, Ly, Lz, L_typeid, params, group_first,
+                              n_group, bussi, stream, true);
     }
 
 extern "C" int cavb200_net_force_add_rank1(cavb200_handle* h, double* net_force, const double* charge, const double* pos,

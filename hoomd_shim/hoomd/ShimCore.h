@@ -225,7 +225,7 @@ class ParticleData
     ParticleData(unsigned int N, const BoxDim& box, const std::vector<std::string>& types,
                  std::shared_ptr<ExecutionConfiguration> exec)
         : m_N(N), m_box(box), m_types(types), m_exec(exec), m_pos(N, exec), m_vel(N, exec),
-          m_accel(N, exec), m_charge(N, exec), m_image(N, exec), m_tag(N, exec)
+          m_accel(N, exec), m_charge(N, exec), m_image(N, exec), m_tag(N, exec), m_net_force(N, exec)
         {
         ArrayHandle<unsigned int> h_tag(m_tag, access_location::host, access_mode::overwrite);
         for (unsigned int i = 0; i < N; i++)
@@ -242,6 +242,8 @@ class ParticleData
     const GPUArray<Scalar>& getCharges() const { return m_charge; }
     const GPUArray<int3>& getImages() const { return m_image; }
     const GPUArray<unsigned int>& getTags() const { return m_tag; }
+    //! sum of all ForceCompute arrays, formed by the integrator between step one and step two
+    const GPUArray<Scalar4>& getNetForce() const { return m_net_force; }
     unsigned int getNTypes() const { return (unsigned int)m_types.size(); }
     unsigned int getTypeByName(const std::string& name) const
         {
@@ -261,6 +263,7 @@ class ParticleData
     GPUArray<Scalar> m_charge;
     GPUArray<int3> m_image;
     GPUArray<unsigned int> m_tag;
+    GPUArray<Scalar4> m_net_force;
     };
 
 class SystemDefinition

@@ -99,7 +99,19 @@ uint64_t cavb200_fault_count(const cavb200_handle* h);
 /* Debug: with tuning "stamps" = 1 the cooperative kernel records, per CTA, globaltimer ns at
  * {start, after reduce, after barrier, after combine, after apply}; out = uint64[8*n_ctas]. */
 int cavb200_debug_stamps(cavb200_handle* h, uint64_t* out, uint32_t n_ctas);
-/* Tuning knobs ("force_ctas_per_sm", "force_threads", "variant", ...); unknown key -> 1. */
+/* Measurement helpers (bench.py, tools/; never on the product path):
+ *   cavb200_debug_delay        a one-thread kernel that holds `stream` for `ns` nanoseconds (<= 100 ms), so that a timed
+ *                              region can be enqueued completely before its first kernel starts
+ *   cavb200_debug_fp64_peak    DFMA microbenchmark on the handle's device: FP64 fused multiply-adds per second over all
+ *                              SMs (the roofline denominator of the F(k,t) kernel); synchronous, ~50 ms
+ *   cavb200_debug_launch_ring  with tuning "stamps" = 2 the persistent kernels record, per launch, {first CTA start,
+ *                              last CTA end} in globaltimer ns into a ring of 2048 pairs indexed by the launch's epoch;
+ *                              out = uint64[2*n_pairs] (may be NULL), *epoch = epoch of the last launch; reset != 0
+ *                              re-arms the ring.  Synchronises the device. */
+int cavb200_debug_delay(cavb200_handle* h, uint64_t ns, void* stream);
+int cavb200_debug_fp64_peak(cavb200_handle* h, double* dfma_per_s);
+int cavb200_debug_launch_ring(cavb200_handle* h, int reset, uint64_t* out, uint32_t n_pairs, uint64_t* epoch);
+/* Tuning knobs ("variant", "threads", "ctas_per_sm", "unroll", "pdl", "stamps", ...); unknown key -> 1. */
 int cavb200_set_tuning(cavb200_handle* h, const char* key, int value);
 int cavb200_get_tuning(const cavb200_handle* h, const char* key, int* value);
 
@@ -175,6 +187,18 @@ int cavb200_nvt_step_one(cavb200_handle* h, double* pos, double* vel, const doub
 int cavb200_nvt_step_two(cavb200_handle* h, double* vel, const double* force, uint32_t N, double dt,
                          uint32_t group_first, uint32_t n_group, void* stream);
 
+/* The same steps with the BOX WRAP of the drift (r <- r + v dt, then wrap): after the drift a
+ * coordinate at or above L/2 moves down by L and its image flag goes up by one, a coordinate below -L/2 the other way
+ * (HOOMD's BoxDim::wrap for an orthorhombic, fully periodic box; upstream code restated from its definition, oracle
+ * orc_wrap).  `image` (int32[3*N]) is read and, for particles that cross a face, written.  The unwrapped position
+ * pos + image * L that the dipole uses (reference src/CavityForceCompute.cc:107-109) is unchanged by the wrap up to one
+ * rounding.  plugin/src/TwoStepConstantVolumeCavity binds these to HOOMD's integrateStepOne / integrateStepTwo. */
+int cavb200_nve_kick_drift_wrap(cavb200_handle* h, double* pos, double* vel, const double* force, int32_t* image, uint32_t N,
+                                double dt, double Lx, double Ly, double Lz, void* stream);
+int cavb200_nvt_step_one_wrap(cavb200_handle* h, double* pos, double* vel, const double* force, int32_t* image, uint32_t N,
+                              double dt, double Lx, double Ly, double Lz, uint32_t group_first, uint32_t n_group,
+                              const cavb200_bussi_args* bussi, void* stream);
+
 /* ---- rank-1 cavity force -------------------------------------------------------
  * Every molecular particle's cavity force is the same 2-vector times its charge,
  *     F_i = (-couplstr * charge_i) * Dq,   Dq = q_xy + (g/K) d_xy
@@ -223,6 +247,19 @@ int cavb200_md_step_fused(cavb200_handle* h, double* pos, double* vel, const dou
 int cavb200_nvt_step_two_rank1(cavb200_handle* h, double* vel, const double* force_other, const double* charge,
                                const double* pos, uint32_t N, double dt, uint32_t L_typeid, double couplstr,
                                uint32_t group_first, uint32_t n_group, void* stream);
+/* ... and with the box wrap + image update after the drift (see cavb200_nvt_step_one_wrap): */
+int cavb200_nvt_step_one_rank1_wrap(cavb200_handle* h, double* pos, double* vel, const double* force_other,
+                                    const double* charge, int32_t* image, uint32_t N, double dt, double Lx, double Ly,
+                                    double Lz, uint32_t L_typeid, double couplstr, uint32_t group_first, uint32_t n_group,
+                                    const cavb200_bussi_args* bussi, void* stream);
+int cavb200_md_step_one_wrap(cavb200_handle* h, double* pos, double* vel, const double* force_other, const double* charge,
+                             int32_t* image, uint32_t N, double dt, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                             const cavb200_params* params, uint32_t group_first, uint32_t n_group,
+                             const cavb200_bussi_args* bussi, void* stream);
+int cavb200_md_step_fused_wrap(cavb200_handle* h, double* pos, double* vel, const double* force_other, const double* charge,
+                               int32_t* image, uint32_t N, double dt, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                               const cavb200_params* params, uint32_t group_first, uint32_t n_group,
+                               const cavb200_bussi_args* bussi, void* stream);
 
 /* ---- device-side trackers ------------------------------------------------------
  * Replace the per-step cpu_local_snapshot of the reference's trackers (reference
@@ -312,6 +349,25 @@ int cavb200_step_host_submit(cavb200_handle* h, uint32_t slot, const double* pos
                              double Lz, uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
                              uint32_t n_group, const cavb200_bussi_args* bussi);
 int cavb200_step_host_wait(cavb200_handle* h, uint32_t slot, double energies[3], double bussi_out[5]);
+/* The same with fewer bytes over PCIe.  flags:
+ *   CAVB200_HOST_KEEP_CHARGE   the charges are unchanged since this slot's last submit (they never change in an MD run:
+ *                              reference examples/05_advanced_run.py:502 sets them once): not uploaded, `charge` may be NULL
+ *   CAVB200_HOST_KEEP_IMAGE    the same for the image flags (they change only when a particle crosses the box)
+ *   CAVB200_HOST_RANK1_RESULT  the cavity force is rank-1, F_i = (-couplstr charge_i) Dq (reference
+ *                              src/CavityForceCompute.cc:183,188-200): return {Dq[2], F_L[3], photon index} (and the
+ *                              energies) through cavb200_step_host_wait_ex instead of the 32 B/particle force array
+ *                              (`force` may be NULL; nothing is written per particle on the device either)
+ * KEEP_* need an earlier submit of the same N on the slot (else cudaErrorInvalidValue).  Velocities and positions are
+ * always moved.  rank1_out = {Dq.x, Dq.y, F_L.x, F_L.y, F_L.z, photon index}; may be NULL. */
+#define CAVB200_HOST_KEEP_CHARGE 1u
+#define CAVB200_HOST_KEEP_IMAGE 2u
+#define CAVB200_HOST_RANK1_RESULT 4u
+int cavb200_step_host_submit_ex(cavb200_handle* h, uint32_t slot, const double* pos, const double* charge,
+                                const int32_t* image, double* force, double* vel, uint32_t N, double Lx, double Ly,
+                                double Lz, uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,
+                                uint32_t n_group, const cavb200_bussi_args* bussi, uint32_t flags);
+int cavb200_step_host_wait_ex(cavb200_handle* h, uint32_t slot, double energies[3], double bussi_out[5],
+                              double rank1_out[6]);
 int cavb200_step_host(cavb200_handle* h, const double* pos, const double* charge, const int32_t* image,
                       double* force, double* vel, uint32_t N, double Lx, double Ly, double Lz,
                       uint32_t L_typeid, const cavb200_params* params, uint32_t group_first,

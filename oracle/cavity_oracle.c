@@ -237,11 +237,46 @@ void orc_rhok(const double* pos, uint32_t stride, uint32_t N, const double* kvec
         }
     }
 
+/* HOOMD's BoxDim::wrap for an orthorhombic box periodic in x, y, z: the box is [-L/2, L/2); a coordinate at or above
+ * the upper face moves down by L and its image flag goes up by one, a coordinate below the lower face the other way;
+ * one shift per direction.  [HOOMD-upstream: not in the reference tree, restated from its definition; it is the
+ * "wrap" of SURVEY.md 8a row a11, the step after r <- r + v dt in TwoStepConstantVolume::integrateStepOne.] */
+void orc_wrap(double* p, int32_t* img, const double L[3])
+    {
+    for (int c = 0; c < 3; c++)
+        {
+        const double hi = 0.5 * L[c];
+        if (p[c] >= hi)
+            {
+            p[c] = p[c] - L[c];
+            img[c] += 1;
+            }
+        else if (p[c] < -hi)
+            {
+            p[c] = p[c] + L[c];
+            img[c] -= 1;
+            }
+        }
+    }
+
+void orc_nve_step_w(double* pos4, double* vel4, const double* charge, int32_t* image3,
+                    double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                    double omegac, double couplstr, double phmass, double dt, double energies[3], int wrap);
+
 void orc_nve_step(double* pos4, double* vel4, const double* charge, const int32_t* image3,
                   double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
                   double omegac, double couplstr, double phmass, double dt, double energies[3])
     {
+    orc_nve_step_w(pos4, vel4, charge, (int32_t*)image3, force4, N, Lx, Ly, Lz, L_typeid, omegac, couplstr, phmass, dt,
+                   energies, 0);
+    }
+
+void orc_nve_step_w(double* pos4, double* vel4, const double* charge, int32_t* image3,
+                    double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                    double omegac, double couplstr, double phmass, double dt, double energies[3], int wrap)
+    {
     double dip[3];
+    const double Lbox[3] = {Lx, Ly, Lz};
     /* half kick + drift with the force from the previous call */
     for (uint32_t i = 0; i < N; i++)
         {
@@ -254,6 +289,8 @@ void orc_nve_step(double* pos4, double* vel4, const double* charge, const int32_
             v[c] = v[c] + hm * f[c];
             p[c] = p[c] + dt * v[c];
             }
+        if (wrap)
+            orc_wrap(p, image3 + 3 * (size_t)i, Lbox);
         }
     orc_cavity_force(pos4, charge, image3, force4, N, Lx, Ly, Lz, L_typeid, omegac, couplstr,
                      phmass, energies, dip);
@@ -267,13 +304,30 @@ void orc_nve_step(double* pos4, double* vel4, const double* charge, const int32_
         }
     }
 
+double orc_nvt_step_w(double* pos4, double* vel4, const double* charge, int32_t* image3,
+                      double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                      double omegac, double couplstr, double phmass, double dt, uint32_t first, uint32_t n,
+                      double dof, double set_T, double tau, double r_normal, double gamma_draw,
+                      double reservoir[2], double* ke_io, double energies[3], int wrap);
+
 double orc_nvt_step(double* pos4, double* vel4, const double* charge, const int32_t* image3,
                     double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
                     double omegac, double couplstr, double phmass, double dt, uint32_t first, uint32_t n,
                     double dof, double set_T, double tau, double r_normal, double gamma_draw,
                     double reservoir[2], double* ke_io, double energies[3])
     {
+    return orc_nvt_step_w(pos4, vel4, charge, (int32_t*)image3, force4, N, Lx, Ly, Lz, L_typeid, omegac, couplstr, phmass, dt,
+                          first, n, dof, set_T, tau, r_normal, gamma_draw, reservoir, ke_io, energies, 0);
+    }
+
+double orc_nvt_step_w(double* pos4, double* vel4, const double* charge, int32_t* image3,
+                      double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                      double omegac, double couplstr, double phmass, double dt, uint32_t first, uint32_t n,
+                      double dof, double set_T, double tau, double r_normal, double gamma_draw,
+                      double reservoir[2], double* ke_io, double energies[3], int wrap)
+    {
     double dip[3];
+    const double Lbox[3] = {Lx, Ly, Lz};
     double alpha = 1.0;
     const double ke = *ke_io;
     if (n > 0 && dof != 0.0)
@@ -301,6 +355,8 @@ double orc_nvt_step(double* pos4, double* vel4, const double* charge, const int3
             v[c] = vc;
             p[c] = p[c] + dt * vc;
             }
+        if (wrap)
+            orc_wrap(p, image3 + 3 * (size_t)i, Lbox);
         }
     orc_cavity_force(pos4, charge, image3, force4, N, Lx, Ly, Lz, L_typeid, omegac, couplstr,
                      phmass, energies, dip);

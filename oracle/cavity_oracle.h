@@ -72,6 +72,17 @@ void orc_rhok(const double* pos, uint32_t stride, uint32_t N, const double* kvec
 /* One velocity-Verlet step of the minimal NVE harness used for the 10k-step drift comparison
  * (cavity force only, all particles incl. photon; masses in vel4.w; positions unwrapped, images
  * untouched).  Not a reference function: the harness both arms share. */
+/* HOOMD BoxDim::wrap, orthorhombic fully periodic box [-L/2, L/2) (upstream code, restated; see the .c file) */
+void orc_wrap(double* p, int32_t* img, const double L[3]);
+/* the two harness steps with the drift followed by the box wrap + image update (wrap != 0) */
+void orc_nve_step_w(double* pos4, double* vel4, const double* charge, int32_t* image3,
+                    double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                    double omegac, double couplstr, double phmass, double dt, double energies[3], int wrap);
+double orc_nvt_step_w(double* pos4, double* vel4, const double* charge, int32_t* image3,
+                      double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
+                      double omegac, double couplstr, double phmass, double dt, uint32_t first, uint32_t n,
+                      double dof, double set_T, double tau, double r_normal, double gamma_draw,
+                      double reservoir[2], double* ke_io, double energies[3], int wrap);
 void orc_nve_step(double* pos4, double* vel4, const double* charge, const int32_t* image3,
                   double* force4, uint32_t N, double Lx, double Ly, double Lz, uint32_t L_typeid,
                   double omegac, double couplstr, double phmass, double dt, double energies[3]);

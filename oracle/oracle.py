@@ -80,6 +80,12 @@ class COracle:
         L.orc_nve_step.restype = None
         L.orc_nve_step.argtypes = [_dp, _dp, _dp, _ip, _dp, C.c_uint32, C.c_double, C.c_double, C.c_double,
                                    C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double, _dp]
+        L.orc_nvt_step_w.restype = C.c_double
+        L.orc_nvt_step_w.argtypes = L.orc_nvt_step.argtypes + [C.c_int]
+        L.orc_nve_step_w.restype = None
+        L.orc_nve_step_w.argtypes = L.orc_nve_step.argtypes + [C.c_int]
+        L.orc_wrap.restype = None
+        L.orc_wrap.argtypes = [_dp, _ip, _dp]
 
     def cavity_force(self, pos, charge, image, box, L_typeid, omegac, couplstr, phmass=1.0):
         """-> dict(force[N,4], energies[3], dipole[3], photon_idx)"""
@@ -122,20 +128,32 @@ class COracle:
         return re + 1j * im
 
     def nvt_step(self, pos, vel, charge, image, force, box, L_typeid, omegac, couplstr, phmass, dt, first, n, dof, kT,
-                 tau, r_normal, gamma_draw, reservoir, ke_io):
-        """One thermostatted harness step (orc_nvt_step); reservoir = float64[2], ke_io = float64[1], both
-        updated in place.  Returns (alpha, energies)."""
+                 tau, r_normal, gamma_draw, reservoir, ke_io, wrap=False):
+        """One thermostatted harness step (orc_nvt_step_w); reservoir = float64[2], ke_io = float64[1], both
+        updated in place; wrap: box wrap + image update after the drift (image is then updated in place).
+        Returns (alpha, energies)."""
         en = np.zeros(3)
-        alpha = self.lib.orc_nvt_step(_d(pos), _d(vel), _d(charge), _i(image), _d(force), pos.shape[0], box[0], box[1],
-                                      box[2], L_typeid, omegac, couplstr, phmass, dt, first, n, dof, kT, tau, r_normal,
-                                      gamma_draw, _d(reservoir), _d(ke_io), _d(en))
+        alpha = self.lib.orc_nvt_step_w(_d(pos), _d(vel), _d(charge), _i(image), _d(force), pos.shape[0], box[0], box[1],
+                                        box[2], L_typeid, omegac, couplstr, phmass, dt, first, n, dof, kT, tau, r_normal,
+                                        gamma_draw, _d(reservoir), _d(ke_io), _d(en), int(wrap))
         return alpha, en
 
-    def nve_step(self, pos, vel, charge, image, force, box, L_typeid, omegac, couplstr, phmass, dt):
+    def nve_step(self, pos, vel, charge, image, force, box, L_typeid, omegac, couplstr, phmass, dt, wrap=False):
         en = np.zeros(3)
-        self.lib.orc_nve_step(_d(pos), _d(vel), _d(charge), _i(image), _d(force), pos.shape[0], box[0], box[1],
-                              box[2], L_typeid, omegac, couplstr, phmass, dt, _d(en))
+        self.lib.orc_nve_step_w(_d(pos), _d(vel), _d(charge), _i(image), _d(force), pos.shape[0], box[0], box[1],
+                                box[2], L_typeid, omegac, couplstr, phmass, dt, _d(en), int(wrap))
         return en
+
+    def wrap(self, pos, image, box):
+        """HOOMD BoxDim::wrap restated (orthorhombic, periodic): pos[N,>=3] and image[N,3] in place."""
+        L = np.ascontiguousarray(box, dtype=np.float64)
+        stride = pos.shape[1]
+        for i in range(pos.shape[0]):
+            p = np.ascontiguousarray(pos[i, :3])
+            im = np.ascontiguousarray(image[i])
+            self.lib.orc_wrap(_d(p), _i(im), _d(L))
+            pos[i, :3] = p
+            image[i] = im
 
 
 class RefOracle:

@@ -4,6 +4,7 @@
 // (SystemDefinition, ForceCompute, Variant, ParticleGroup, ComputeThermo, Thermostat).  A real
 // deployment never builds this file (plugin/CMakeLists.txt).
 #include "hoomd/ShimCore.h"
+#include "hoomd/md/IntegrationMethodTwoStep.h"
 #include "hoomd/md/Thermostat.h"
 
 #include <pybind11/numpy.h>
@@ -62,6 +63,16 @@ PYBIND11_MODULE(_hoomd_shim, m)
                  ArrayHandle<int3> h(p.getImages(), access_location::host, access_mode::overwrite);
                  std::memcpy((void*)h.data, a.data(), sizeof(int) * 3 * (size_t)p.getN());
              })
+        .def("setNetForce", [](ParticleData& p, py::array_t<double, py::array::c_style | py::array::forcecast> a)
+             { fill<Scalar4, 4>(p.getNetForce(), a, p.getN()); })
+        .def("getImages",
+             [](ParticleData& p)
+             {
+                 ArrayHandle<int3> h(p.getImages(), access_location::host, access_mode::read);
+                 py::array_t<int> out({(py::ssize_t)p.getN(), (py::ssize_t)3});
+                 std::memcpy(out.mutable_data(), (const void*)h.data, sizeof(int) * 3 * (size_t)p.getN());
+                 return out;
+             })
         .def("getVelocities", [](ParticleData& p) { return fetch<Scalar4, 4>(p.getVelocities(), p.getN()); })
         .def("getPositions", [](ParticleData& p) { return fetch<Scalar4, 4>(p.getPositions(), p.getN()); });
 
@@ -94,6 +105,11 @@ PYBIND11_MODULE(_hoomd_shim, m)
         .def("compute", &md::ComputeThermo::compute)
         .def("getTranslationalKineticEnergy", &md::ComputeThermo::getTranslationalKineticEnergy)
         .def("setRotationalKineticEnergy", &md::ComputeThermo::setRotationalKineticEnergy);
+
+    py::class_<md::IntegrationMethodTwoStep, std::shared_ptr<md::IntegrationMethodTwoStep>>(m, "IntegrationMethodTwoStep")
+        .def("integrateStepOne", &md::IntegrationMethodTwoStep::integrateStepOne)
+        .def("integrateStepTwo", &md::IntegrationMethodTwoStep::integrateStepTwo)
+        .def("setDeltaT", &md::IntegrationMethodTwoStep::setDeltaT);
 
     py::class_<md::Thermostat, std::shared_ptr<md::Thermostat>>(m, "Thermostat")
         .def("getRescalingFactorsOne", &md::Thermostat::getRescalingFactorsOne)

@@ -27,6 +27,8 @@
 #include <hoomd/md/ComputeThermo.h>
 #include <hoomd/md/Thermostat.h>
 
+#include "CavbHooks.h"
+
 #include <array>
 #include <cavb200.h>
 #include <cmath>
@@ -36,7 +38,7 @@
 
 namespace hoomd::md
     {
-class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat
+class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat, public CavbBussiSource
     {
     public:
     BussiReservoirThermostat(std::shared_ptr<Variant> T, std::shared_ptr<ParticleGroup> group,
@@ -133,6 +135,30 @@ class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat
         return {factor, rotational_factor};
         }
 
+    //! CavbBussiSource: the draws of one step for a fused integration method (TwoStepConstantVolumeCavity), which forms
+    //! alpha on the device from the kinetic energy its own step two left there
+    cavb200_bussi_args drawBussiArgs(uint64_t timestep, double deltaT) override
+        {
+        const Scalar translational_dof = m_group->getTranslationalDOF();
+        if (m_group->getRotationalDOF() != 0)
+            throw std::runtime_error("BussiReservoirThermostat (cavb200): the fused integration method handles point "
+                                     "particles only (rotational degrees of freedom present)");
+        unsigned int instance_id = 0;
+        if (m_group->getNumMembersGlobal() > 0)
+            instance_id = m_group->getMemberTag(0);
+        RandomGenerator rng(Seed(RNGIdentifier::BussiThermostat, timestep, m_sysdef->getSeed()), instance_id);
+        double r_normal = 0.0, gamma_draw = 0.0;
+        draw(rng, translational_dof, r_normal, gamma_draw);
+        cavb200_bussi_args a = {m_T->operator()(timestep), m_tau, deltaT, translational_dof, r_normal, gamma_draw};
+        m_stale = true;
+        return a;
+        }
+    void adoptHandle(cavb200_handle* h) override
+        {
+        m_read_handle = h ? h : m_handle;
+        m_stale = true;
+        }
+
     Scalar getTau() const { return m_tau; }
     void setTau(Scalar tau) { m_tau = tau; }
     bool getFusedRescale() const { return m_fused; }
@@ -168,6 +194,8 @@ class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat
         m_dev_cumulative = 0.0;
         if (m_handle)
             cavb200_bussi_reset(m_handle, nullptr);
+        if (m_read_handle && m_read_handle != m_handle)
+            cavb200_bussi_reset(m_read_handle, nullptr);
         m_stale = false;
         }
 
@@ -223,7 +251,7 @@ class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat
         if (!m_stale)
             return;
         double out[5];
-        check(cavb200_bussi_read(m_handle, out, nullptr));
+        check(cavb200_bussi_read(m_read_handle ? m_read_handle : m_handle, out, nullptr));
         if (out[4] == 1.0)
             throw std::runtime_error("Bussi thermostat requires non-zero initial momenta.");
         m_instantaneous_reservoir_translational = out[2];
@@ -234,6 +262,7 @@ class PYBIND11_EXPORT BussiReservoirThermostat : public Thermostat
 
     Scalar m_tau;
     cavb200_handle* m_handle;
+    cavb200_handle* m_read_handle = nullptr; //!< handle of a fused integration method that adopted this thermostat
     bool m_fused;
     bool m_stale;
     Scalar m_host_cumulative = 0.0; //!< deltas accumulated by the host path

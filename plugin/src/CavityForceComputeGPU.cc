@@ -1,6 +1,8 @@
 // CavityForceComputeGPU.cc -- see the header.  No CPU fallback: a failure of the CUDA path throws.
 #include "CavityForceComputeGPU.h"
 
+#include <cuda_runtime.h>
+
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -70,10 +72,23 @@ pybind11::dict CavityForceComputeGPU::getParams()
     return v;
     }
 
+void CavityForceComputeGPU::useHandle(cavb200_handle* h, int mode)
+    {
+    if (mode != 0 && !h)
+        throw std::runtime_error("CavityForceComputeGPU::useHandle: rank-1 modes need the integration method's handle");
+    m_ext_handle = mode ? h : nullptr;
+    m_mode = mode;
+    m_integrator_reduced = false;
+    m_zeroed = false;
+    m_fresh = false;
+    }
+
 void CavityForceComputeGPU::computeForces(uint64_t timestep)
     {
     (void)timestep;
     const unsigned int N = m_pdata->getN();
+    if (m_mode == 2 && m_integrator_reduced)
+        return; // the integration method's step one has already reduced the dipole of these positions
     // 'L' missing from the type list: the reference GPU class reports zero energies and leaves the
     // forces zero (src/CavityForceComputeGPU.cc:114-123); UINT32_MAX asks the library for exactly that
     uint32_t L_typeid = 0xFFFFFFFFu;
@@ -90,6 +105,23 @@ void CavityForceComputeGPU::computeForces(uint64_t timestep)
     ArrayHandle<Scalar4> d_pos(m_pdata->getPositions(), access_location::device, access_mode::read);
     ArrayHandle<Scalar> d_charge(m_pdata->getCharges(), access_location::device, access_mode::read);
     ArrayHandle<int3> d_image(m_pdata->getImages(), access_location::device, access_mode::read);
+    if (m_mode != 0)
+        {
+        // rank-1: the contribution to HOOMD's net force is zero (m_force was zero-initialised by ForceCompute and is
+        // zeroed once here in case the object ran in stored mode before); Dq / F_L stay on the method's handle
+        if (!m_zeroed)
+            {
+            ArrayHandle<Scalar4> d_f(m_force, access_location::device, access_mode::overwrite);
+            cudaMemsetAsync(d_f.data, 0, sizeof(Scalar4) * (size_t)N, (cudaStream_t)m_stream);
+            m_zeroed = true;
+            }
+        check(cavb200_force_rank1(m_ext_handle, reinterpret_cast<const double*>(d_pos.data), d_charge.data,
+                                  reinterpret_cast<const int32_t*>(d_image.data), N, L.x, L.y, L.z, L_typeid, &m_params,
+                                  m_stream),
+              "cavb200_force_rank1");
+        m_fresh = false;
+        return;
+        }
     ArrayHandle<Scalar4> d_force(m_force, access_location::device, access_mode::overwrite);
 
     // HOOMD runs its kernels on the legacy default stream: stream 0 ordering is the contract
@@ -105,7 +137,8 @@ void CavityForceComputeGPU::readBack()
     if (m_fresh)
         return;
     int32_t photon = -1;
-    check(cavb200_force_read(m_handle, m_energies, m_dipole, &photon, m_stream), "cavb200_force_read");
+    check(cavb200_force_read(m_ext_handle ? m_ext_handle : m_handle, m_energies, m_dipole, &photon, m_stream),
+          "cavb200_force_read");
     m_fresh = true;
     }
 

@@ -57,6 +57,15 @@ class PYBIND11_EXPORT CavityForceComputeGPU : public ForceCompute
     //! newest min(max_records, stored) records, oldest first: list of 16-tuples (layout: include/cavb200.h)
     pybind11::list trackRead(unsigned int max_records);
 
+    //! Used by TwoStepConstantVolumeCavity.  mode 0: back to normal (own handle, forces stored).
+    //! mode 1: rank-1 -- the dipole reduce runs on the integration method's handle `h` and NOTHING is written per
+    //! particle: m_force stays zero, the method's kicks form F_i = (-g c_i) Dq from the charge
+    //! (reference src/CavityForceCompute.cc:183,188-200).  mode 2: as 1, and the method's own step-one kernel reduces the
+    //! dipole of the new positions, so computeForces only runs the reduce until the method has taken over.
+    void useHandle(cavb200_handle* h, int mode);
+    void integratorHasReduced() { m_integrator_reduced = true; m_fresh = false; }
+    const cavb200_params& params() const { return m_params; }
+
     protected:
     virtual void computeForces(uint64_t timestep);
 
@@ -68,6 +77,10 @@ class PYBIND11_EXPORT CavityForceComputeGPU : public ForceCompute
     double m_dipole[3];
     bool m_fresh; //!< host copies are current
     void* m_stream = nullptr;
+    cavb200_handle* m_ext_handle = nullptr; //!< the integration method's handle (rank-1 modes), not owned
+    int m_mode = 0;
+    bool m_integrator_reduced = false;
+    bool m_zeroed = false;
     };
 
 namespace detail

@@ -255,6 +255,58 @@ def test_step_host_pipelined_slots(handle, coracle):
         handle.step_host_wait(99)
 
 
+def test_step_host_reduced_copies(handle, coracle):
+    """cavb200_step_host_submit_ex: charges / images flagged "unchanged since the slot's last submit" are not uploaded
+    (the host arrays may then hold anything -- here NaN / garbage), and the rank-1 result {Dq, F_L, photon index} stands
+    in for the force array: F_i = (-g c_i) Dq bit for bit (reference src/CavityForceCompute.cc:183,188-200)."""
+    n_mol = 80000
+    p = capi.Params.make(0.01, 1e-3)
+    s = synth.make_system(n_mol, replica=2)
+    a = bargs(3.0 * n_mol - 3.0)
+    bufs = {k: capi.PinnedArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+    force = capi.PinnedArray((s.N, 4), np.float64)
+    args = (s.N, s.box, s.L_typeid, p, 0, n_mol, a)
+    # KEEP_* without an earlier submit of this size on the slot is refused
+    with pytest.raises(capi.CavbError):
+        handle.step_host_submit_ex(3, bufs["pos"], None, bufs["image"], force, bufs["vel"], *args, handle.HOST_KEEP_CHARGE)
+    handle.bussi_reset()
+    handle.step_host_submit_ex(3, bufs["pos"], bufs["charge"], bufs["image"], force, bufs["vel"], *args, 0)
+    handle.step_host_wait_ex(3)
+    # second step: new positions / velocities, charges and images not sent (and poisoned on the host)
+    rng = np.random.default_rng(5)
+    s2 = s.copy()
+    s2.pos[:, :3] += 0.01 * rng.standard_normal((s.N, 3))
+    bufs["pos"].array[...] = s2.pos
+    s2.vel[...] = bufs["vel"].array  # rescaled by the first step
+    bufs["charge"].array[...] = np.nan
+    bufs["image"].array[...] = 12345
+    ref = coracle.cavity_force(s2.pos, s2.charge, s2.image, s2.box, s2.L_typeid, 0.01, 1e-3)
+    vref = s2.vel.copy()
+    alpha, ke = coracle.bussi_step(vref, np.arange(n_mol, dtype=np.uint32), a.dof, DT, KT, TAU, a.r_normal, a.gamma_draw,
+                                   np.zeros(2))
+    force.array[...] = np.nan
+    handle.step_host_submit_ex(3, bufs["pos"], None, None, force, bufs["vel"], *args,
+                               handle.HOST_KEEP_CHARGE | handle.HOST_KEEP_IMAGE)
+    en, bo, r1 = handle.step_host_wait_ex(3)
+    scale = np.abs(ref["force"]).max()
+    assert np.abs(force.array - ref["force"]).max() <= 1e-10 * scale
+    assert np.allclose(bufs["vel"].array, vref, rtol=1e-12, atol=0) and np.allclose(en, ref["energies"], rtol=1e-10)
+    assert abs(bo["alpha"] - alpha) <= 1e-12 * abs(alpha) and r1["photon_idx"] == ref["photon_idx"]
+    full = force.array.copy()
+    # third call: the same inputs (velocities restored), rank-1 result instead of the force array
+    bufs["vel"].array[...] = s2.vel
+    handle.step_host_submit_ex(3, bufs["pos"], None, None, None, bufs["vel"], *args,
+                               handle.HOST_KEEP_CHARGE | handle.HOST_KEEP_IMAGE | handle.HOST_RANK1_RESULT)
+    en3, bo3, r3 = handle.step_host_wait_ex(3)
+    assert np.array_equal(en3, en) and np.array_equal(r3["Dq"], r1["Dq"]) and np.array_equal(r3["F_L"], r1["F_L"])
+    f1 = np.zeros((s.N, 4))
+    f1[:, 0] = (-1e-3 * s2.charge) * r3["Dq"][0]
+    f1[:, 1] = (-1e-3 * s2.charge) * r3["Dq"][1]
+    f1[r3["photon_idx"], :3] = r3["F_L"]
+    assert np.array_equal(f1, full)  # the stored force IS the rank-1 product
+    assert np.allclose(bufs["vel"].array, vref, rtol=1e-12, atol=0)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("n,first,use_list", [(1, 0, False), (33, 0, False), (1000, 7, False), (262145, 0, False),
                                                (50001, 0, True), (0, 0, False)])

@@ -230,3 +230,94 @@ def test_two_force_objects_on_unordered_streams(mods, coracle, cooperative):
     if cooperative:
         assert thrown == 0 and all(fc.getFaultCount() == 0 for fc, _, _ in objs)
     capi.sync()
+
+
+@pytest.mark.parametrize("mode", ["stored", "rank1", "one_launch"])
+@pytest.mark.parametrize("n_mol", [300, 40000])
+def test_two_step_constant_volume_cavity(mods, coracle, mode, n_mol):
+    """The fused integration method (plugin/src/TwoStepConstantVolumeCavity) driven the way HOOMD's
+    IntegratorTwoStep::update drives a method -- integrateStepOne(t); every force computes; net force; integrateStepTwo(t)
+    -- with the thermostat's draws made through the BussiReservoirThermostat object and the cavity force through the
+    CavityForceComputeGPU object.  Against orc_nvt_step_w (alpha-rescale, kick, drift, box wrap + image update, cavity
+    force, kick) on a box where a large share of the particles crosses a face."""
+    from cav_hoomd_b200 import rng as crng
+    shim, cav, bus = mods
+    s = synth.make_system(n_mol, replica=51)
+    Lbox = s.box[0]
+    mol = s.typeid != s.L_typeid
+    s.vel[mol, :3] *= (Lbox / 6.0) / (np.abs(s.vel[mol, :3]).max() * synth.DT_1FS)
+    steps, dt = 6, synth.DT_1FS
+    dof = 3.0 * n_mol - 3.0
+    sysdef, pd = make_sysdef(shim, s)
+    group = shim.ParticleGroup(sysdef, list(range(n_mol)))
+    group.setTranslationalDOF(dof)
+    th = bus.BussiReservoirThermostat(shim.VariantConstant(synth.KT_100K), group, shim.ComputeThermo(sysdef, group), sysdef,
+                                      synth.TAU_5PS)
+    fc = cav.CavityForceComputeGPU(sysdef, 0.01, 1e-3)
+    method = cav.TwoStepConstantVolumeCavity(sysdef, group, th, fc, mode)
+    assert method.mode == mode
+    method.setDeltaT(dt)
+    draws = [crng.bussi_draws(t, 11, 0, dof) for t in range(steps)]
+
+    # Integrator::prepRun: the forces of the initial configuration
+    fc.compute(0)
+    net = fc.getForces()
+    if mode != "stored":
+        assert not net.any()  # rank-1: nothing is stored, the contribution to the net force is zero
+    pd.setNetForce(net)
+    for t in range(steps):
+        bus._inject_draws(list(draws[t]))
+        method.integrateStepOne(t)
+        fc.compute(t + 1)
+        pd.setNetForce(fc.getForces())
+        method.integrateStepTwo(t)
+    method.flush()
+
+    # oracle
+    pos, vel, image, force = s.pos.copy(), s.vel.copy(), s.image.copy(), np.zeros((s.N, 4))
+    force[:] = coracle.cavity_force(pos, s.charge, image, s.box, s.L_typeid, 0.01, 1e-3)["force"]
+    ke = np.array([coracle.kinetic_energy(vel, np.arange(n_mol, dtype=np.uint32))])
+    res = np.zeros(2)
+    for t in range(steps):
+        a_ref, en_ref = coracle.nvt_step(pos, vel, s.charge, image, force, s.box, s.L_typeid, 0.01, 1e-3, 1.0, dt, 0, n_mol, dof,
+                                         synth.KT_100K, synth.TAU_5PS, draws[t][0], draws[t][1], res, ke, wrap=True)
+    gp, gv, gi = pd.getPositions(), pd.getVelocities(), pd.getImages()
+    assert np.any(image != s.image, axis=1).sum() > 0.2 * s.N and np.array_equal(gi, image)
+    assert np.abs(gp[:, :3] - pos[:, :3]).max() <= 1e-10 * np.abs(pos[:, :3]).max()
+    assert np.abs(gv[:, :3] - vel[:, :3]).max() <= 1e-10 * np.abs(vel[:, :3]).max()
+    # the reference's getters keep working: energies from the force object, reservoir from the thermostat object
+    assert np.isclose(fc.getHarmonicEnergy(), en_ref[0], rtol=1e-10) and np.isclose(fc.getCouplingEnergy(), en_ref[1], rtol=1e-10)
+    assert np.isclose(th.getReservoirEnergyTranslational(), res[0], rtol=1e-9, atol=1e-18)
+    assert np.isclose(th.getInstantaneousReservoirTranslational(), res[1], rtol=1e-9, atol=1e-18)
+    launches = method.getLaunchCount()
+    # stored / rank1: KE once, then two launches per step (+ the force object's own); one_launch: KE, then ONE per step + flush
+    assert launches == {"stored": 1 + 2 * steps, "rank1": 1 + 2 * steps + steps + 1, "one_launch": 1 + steps + 1 + 1}[mode]
+
+
+def test_two_step_method_argument_checks(mods):
+    shim, cav, bus = mods
+    s = synth.make_system(100)
+    sysdef, pd = make_sysdef(shim, s)
+    fc = cav.CavityForceComputeGPU(sysdef, 0.01, 1e-3)
+    gap = shim.ParticleGroup(sysdef, [0, 1, 2, 4, 5])  # not a contiguous range
+    gap.setTranslationalDOF(12.0)
+    with pytest.raises((ValueError, RuntimeError)):
+        cav.TwoStepConstantVolumeCavity(sysdef, gap, None, fc, "bogus")
+    with pytest.raises((ValueError, RuntimeError)):
+        cav.TwoStepConstantVolumeCavity(sysdef, gap, None, None, "rank1")
+    m = cav.TwoStepConstantVolumeCavity(sysdef, gap, None, fc, "stored")
+    m.setDeltaT(1.0)
+    pd.setNetForce(np.zeros((s.N, 4)))
+    with pytest.raises(RuntimeError, match="contiguous"):
+        m.integrateStepOne(0)
+    # no thermostat: plain velocity Verlet with the wrap
+    full = shim.ParticleGroup(sysdef, list(range(100)))
+    m2 = cav.TwoStepConstantVolumeCavity(sysdef, full, None, fc, "stored")
+    m2.setDeltaT(1.0)
+    v0, p0 = pd.getVelocities(), pd.getPositions()
+    m2.integrateStepOne(0)
+    m2.integrateStepTwo(0)
+    assert np.array_equal(pd.getVelocities(), v0)  # zero net force
+    L = np.array(s.box)
+    u = pd.getPositions()[:, :3] + pd.getImages() * L
+    assert np.allclose(u, p0[:, :3] + s.image * L + v0[:, :3], rtol=1e-13, atol=1e-9)
