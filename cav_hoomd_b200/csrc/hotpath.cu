@@ -20,15 +20,17 @@ namespace cavb
 // Per-launch device timestamps (tuning "stamps" = 2; bench.py's kernel_ms_device): the upper quarter of the stamps
 // buffer is a ring of LAUNCH_RING {first CTA start, last CTA end} pairs in globaltimer ns, indexed by the launch's
 // epoch; every CTA contributes one atomicMin and one atomicMax.  cavb200_debug_launch_ring resets / reads it.
-__device__ __forceinline__ void ring_stamp(unsigned long long* stamps, int mode, unsigned long long epoch,
-                                           unsigned long long t_start)
+// (Both stamps are taken by thread 0 inside short branches so that no value stays live across the kernel: the
+// persistent kernels sit exactly at their 80-register budget, and a start time carried to the end cost a spill and
+// 0.4-0.6 us per 1M-particle call.)
+__device__ __forceinline__ void ring_start(unsigned long long* stamps, unsigned long long epoch, unsigned long long t_start)
+    {
+    atomicMin(stamps + LAUNCH_RING_OFFSET + 2ull * (epoch & (LAUNCH_RING - 1)), t_start);
+    }
+__device__ __forceinline__ void ring_end(unsigned long long* stamps, int mode, unsigned long long epoch)
     {
     if (mode == 2 && threadIdx.x == 0)
-        {
-        unsigned long long* r = stamps + LAUNCH_RING_OFFSET + 2ull * (epoch & (LAUNCH_RING - 1));
-        atomicMin(r, t_start);
-        atomicMax(r + 1, globaltimer_ns());
-        }
+        atomicMax(stamps + LAUNCH_RING_OFFSET + 2ull * (epoch & (LAUNCH_RING - 1)) + 1, globaltimer_ns());
     }
 
 // ------------------------------------------------------------------------------------------
@@ -82,15 +84,15 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1) k_apply(ForceIn f, Buss
 // by every CTA before it publishes anything and written back by CTA 0 after its combine -- i.e. after
 // every CTA has published, hence after every CTA has read it.  No host-side state, so the kernel is
 // safe under CUDA-graph replay and for any sequence of grid sizes.
-template<bool FORCE, bool BUSSI, int UNROLL, int LB>
+template<bool FORCE, bool BUSSI, int UNROLL, int LB, bool RING>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_fused(ForceIn f, BussiIn b, Partial* recs, Scalars* scalars, unsigned long long* epoch_ctr,
-            unsigned long long* stamps, int stamp_mode)
+            unsigned long long* stamps)
     {
+    constexpr int stamp_mode = RING ? 2 : 1;
     __shared__ BlockScratch sc;
     // optional phase stamps (tools/phase_stamps.py): thread 0 of every CTA, globaltimer ns
-    unsigned long long* my_stamps = (stamp_mode == 1 && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
-    const unsigned long long t_start = stamp_mode == 2 ? globaltimer_ns() : 0ull;
+    unsigned long long* my_stamps = (!RING && stamps && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
     if (my_stamps)
         my_stamps[0] = globaltimer_ns();
     // programmatic dependent launch: this grid may have been scheduled while the previous kernel of
@@ -98,8 +100,11 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     pdl_wait();
     if (threadIdx.x == 0)
         {
+        const unsigned long long t_start = stamp_mode == 2 ? globaltimer_ns() : 0ull;
         sc.flags = 0u;
         sc.epoch = ld_relaxed_u64(epoch_ctr) + 1ull;
+        if (stamp_mode == 2)
+            ring_start(stamps, sc.epoch, t_start);
         }
     reduce_phase<FORCE, BUSSI, UNROLL>(f, b, sc); // (its barriers also publish sc.epoch to the block)
     if (threadIdx.x == 0)
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         apply_phase<FORCE, BUSSI, UNROLL>(sc.fin, f, b);
     if (my_stamps)
         my_stamps[4] = globaltimer_ns();
-    ring_stamp(stamps, stamp_mode, epoch, t_start);
+    ring_end(stamps, stamp_mode, epoch);
     }
 
 // variant 2 ("split-phase"): the thermostat half and the force half are independent, so their two
@@ -154,21 +159,24 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
 // No CTA ever waits for the slowest CTA of the phase it has just finished.  Measured background
 // (profiles/microwb_r1b.txt): the read half is HBM bound, the write half is bound by L2 store
 // ingest with HBM idle, so a CTA that runs ahead into its write half does not slow the readers.
-template<int UNROLL, int LB>
+template<int UNROLL, int LB, bool RING>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_split(ForceIn f, BussiIn b, Partial* recsF, Partial* recsB, Scalars* scalars, unsigned long long* epoch_ctr,
-            unsigned long long* stamps, int stamp_mode)
+            unsigned long long* stamps)
     {
+    constexpr int stamp_mode = RING ? 2 : 1;
     __shared__ BlockScratch sc;
-    unsigned long long* my_stamps = (stamp_mode == 1 && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
-    const unsigned long long t_start = stamp_mode == 2 ? globaltimer_ns() : 0ull;
+    unsigned long long* my_stamps = (!RING && stamps && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
     if (my_stamps)
         my_stamps[0] = globaltimer_ns();
     pdl_wait();
     if (threadIdx.x == 0)
         {
+        const unsigned long long t_start = stamp_mode == 2 ? globaltimer_ns() : 0ull;
         sc.flags = 0u;
         sc.epoch = ld_relaxed_u64(epoch_ctr) + 1ull;
+        if (stamp_mode == 2)
+            ring_start(stamps, sc.epoch, t_start);
         }
     // dipole first: its hand-off (the heavier combine, and the one whose stragglers matter) then has
     // the whole velocity pass to complete behind; the light KE hand-off hides behind the force writes
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     apply_phase<false, true, UNROLL>(sc.fin, f, b);
     if (my_stamps)
         my_stamps[6] = globaltimer_ns();
-    ring_stamp(stamps, stamp_mode, epoch, t_start);
+    ring_end(stamps, stamp_mode, epoch);
     }
 
 // variant 3 ("split-phase with a folder CTA"): the split-phase schedule, but ONE extra CTA that streams
@@ -220,21 +228,24 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
 //     folder CTA:     fold dipole records -> publish Final(F) | fold KE records -> publish Final(K)
 // The dipole is the correctly rounded sum of the same terms as in the other variants, folded over one
 // record fewer (grid - 1 streaming CTAs): results agree to the last bit or two, not bit for bit.
-template<int UNROLL, int LB, bool KE_FIRST>
+template<int UNROLL, int LB, bool KE_FIRST, bool RING>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_split_folder(ForceIn f, BussiIn b, Partial* recsF, Partial* recsB, Partial* finals, Scalars* scalars,
-                   unsigned long long* epoch_ctr, unsigned long long* stamps, int stamp_mode)
+                   unsigned long long* epoch_ctr, unsigned long long* stamps)
     {
+    constexpr int stamp_mode = RING ? 2 : 1;
     __shared__ BlockScratch sc;
-    unsigned long long* my_stamps = (stamp_mode == 1 && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
-    const unsigned long long t_start = stamp_mode == 2 ? globaltimer_ns() : 0ull;
+    unsigned long long* my_stamps = (!RING && stamps && threadIdx.x == 0) ? stamps + 8ull * blockIdx.x : nullptr;
     if (my_stamps)
         my_stamps[0] = globaltimer_ns();
     pdl_wait();
     if (threadIdx.x == 0)
         {
+        const unsigned long long t_start = stamp_mode == 2 ? globaltimer_ns() : 0ull;
         sc.flags = 0u;
         sc.epoch = ld_relaxed_u64(epoch_ctr) + 1ull;
+        if (stamp_mode == 2)
+            ring_start(stamps, sc.epoch, t_start);
         }
     StreamGrid g;
     g.nblk = gridDim.x - 1;
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
                 *epoch_ctr = epoch; // every streaming CTA has published twice, hence read the counter
             }
         pdl_launch_dependents();
-        ring_stamp(stamps, stamp_mode, epoch, t_start);
+        ring_end(stamps, stamp_mode, epoch);
         return;
         }
     // ---- streaming CTAs ----
@@ -396,7 +407,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         }
     if (my_stamps)
         my_stamps[6] = globaltimer_ns();
-    ring_stamp(stamps, stamp_mode, epoch, t_start);
+    ring_end(stamps, stamp_mode, epoch);
     }
 
 // ------------------------------------------------------------------------------------------
@@ -444,16 +455,26 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         // the folder pays two extra L2 round trips, which only a full streaming grid hides (65k particles:
         // 11.95 us with the folder, 10.1 us without): small systems take the plain split-phase kernel
         const bool folder = h->tune.variant == 3 && want >= (unsigned long long)max_grid;
-        const void* kern = !folder ? (const void*)k_split<UNROLL, LB>
-                                   : (h->tune.ke_first ? (const void*)k_split_folder<UNROLL, LB, true>
-                                                       : (const void*)k_split_folder<UNROLL, LB, false>);
+        // (the per-launch timestamp ring, tuning stamps = 2, is a separate instantiation: the kernels sit exactly at their
+        // 80-register budget and even a runtime switch for it cost spills and ~0.5 us per 1M-particle call)
+        const bool ring = h->tune.stamps == 2;
+        const void* kern;
         int per_sm = 0;
         if (folder && h->tune.ke_first)
-            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split_folder<UNROLL, LB, true>, threads, 0));
+            {
+            kern = ring ? (const void*)k_split_folder<UNROLL, LB, true, true> : (const void*)k_split_folder<UNROLL, LB, true, false>;
+            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split_folder<UNROLL, LB, true, false>, threads, 0));
+            }
         else if (folder)
-            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split_folder<UNROLL, LB, false>, threads, 0));
+            {
+            kern = ring ? (const void*)k_split_folder<UNROLL, LB, false, true> : (const void*)k_split_folder<UNROLL, LB, false, false>;
+            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split_folder<UNROLL, LB, false, false>, threads, 0));
+            }
         else
-            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split<UNROLL, LB>, threads, 0));
+            {
+            kern = ring ? (const void*)k_split<UNROLL, LB, true> : (const void*)k_split<UNROLL, LB, false>;
+            CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_split<UNROLL, LB, false>, threads, 0));
+            }
         if (per_sm < 1)
             return (int)cudaErrorLaunchOutOfResources;
         if (max_grid > per_sm * h->num_sms)
@@ -472,10 +493,9 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         unsigned long long* arr = h->counters + 2;
         ForceIn ff = f;
         BussiIn bb = b;
-        unsigned long long* stamps = h->stamps;
-        int stamp_mode = h->tune.stamps;
-        void* args_split[] = {&ff, &bb, &recsF, &recsB, &sca, &arr, &stamps, &stamp_mode};
-        void* args_folder[] = {&ff, &bb, &recsF, &recsB, &finals, &sca, &arr, &stamps, &stamp_mode};
+        unsigned long long* stamps = h->tune.stamps ? h->stamps : nullptr;
+        void* args_split[] = {&ff, &bb, &recsF, &recsB, &sca, &arr, &stamps};
+        void* args_folder[] = {&ff, &bb, &recsF, &recsB, &finals, &sca, &arr, &stamps};
         void** args = folder ? args_folder : args_split;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
@@ -532,7 +552,8 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
     if (h->tune.variant >= 1 && h->coop_supported)
         {
         int per_sm = 0;
-        CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<FORCE, BUSSI, UNROLL, LB>, threads, 0));
+        const bool ring = h->tune.stamps == 2;
+        CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<FORCE, BUSSI, UNROLL, LB, false>, threads, 0));
         if (per_sm < 1)
             return (int)cudaErrorLaunchOutOfResources;
         int resident = per_sm * h->num_sms;
@@ -544,9 +565,8 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         unsigned long long* arr = h->counters + 2;
         ForceIn ff = f;
         BussiIn bb = b;
-        unsigned long long* stamps = h->stamps;
-        int stamp_mode = h->tune.stamps;
-        void* args[] = {&ff, &bb, &recs, &sca, &arr, &stamps, &stamp_mode};
+        unsigned long long* stamps = h->tune.stamps ? h->stamps : nullptr;
+        void* args[] = {&ff, &bb, &recs, &sca, &arr, &stamps};
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(threads);
@@ -571,7 +591,8 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
             }
         cfg.attrs = attrs;
         cfg.numAttrs = na;
-        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_fused<FORCE, BUSSI, UNROLL, LB>, args));
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, ring ? (const void*)k_fused<FORCE, BUSSI, UNROLL, LB, true>
+                                                  : (const void*)k_fused<FORCE, BUSSI, UNROLL, LB, false>, args));
         h->launches += 1;
         return 0;
         }

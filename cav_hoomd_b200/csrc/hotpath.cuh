@@ -201,9 +201,60 @@ __device__ __forceinline__ StreamGrid whole_grid()
 // round trips per loop iteration as first written (18.0 vs 16.1 us per 1M-particle Bussi call, profiles/ab_r2b.txt).
 // The index loads are therefore software-pipelined one iteration ahead -- the indices of iteration i+1 are requested
 // together with the velocities of iteration i -- so only the first iteration pays the second round trip.
+// (The list paths are separate, non-inlined functions: inlined, their loops changed the register allocation of the
+// persistent kernels around them -- which sit exactly at their 80-register budget -- and cost the contiguous step
+// 0.3 us at 1M particles.  One call per kernel launch.)
+template<int UNROLL> __device__ __noinline__ double reduce_ke_list(const BussiIn b, const StreamGrid g)
+    {
+    constexpr int U = UNROLL > 1 ? UNROLL : 1;
+    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
+    unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
+    const unsigned long long n = b.n;
+    double ke[U];
+    unsigned int nxt[U];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+        {
+        ke[k] = 0.0;
+        nxt[k] = (j + k * stride < n) ? __ldg(b.gidx + j + k * stride) : 0u;
+        }
+    for (; j < n; j += U * stride)
+        {
+        double4 v[U];
+        unsigned int cur[U];
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            {
+            cur[k] = nxt[k];
+            v[k] = make_double4(0.0, 0.0, 0.0, 0.0);
+            if (j + k * stride < n)
+                v[k] = ld256(b.vel + cur[k]);
+            }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            {
+            const unsigned long long jn = j + (U + k) * stride;
+            nxt[k] = jn < n ? __ldg(b.gidx + jn) : 0u;
+            }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z); // (+0 for the padding slots)
+        }
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < U; k++)
+        sum += ke[k];
+    return sum;
+    }
+
 template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const BussiIn& b, const StreamGrid g = whole_grid())
     {
     constexpr int U = UNROLL > 1 ? UNROLL : 1;
+    if (b.gidx)
+        {
+        a.ke += reduce_ke_list<UNROLL>(b, g);
+        return;
+        }
     const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
     unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     const unsigned long long n = b.n;
@@ -211,52 +262,20 @@ template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const Bus
 #pragma unroll
     for (int k = 0; k < U; k++)
         ke[k] = 0.0;
-    if (b.gidx)
+    for (; j + (U - 1) * stride < n; j += U * stride)
         {
-        unsigned int nxt[U];
+        double4 v[U];
 #pragma unroll
         for (int k = 0; k < U; k++)
-            nxt[k] = (j + k * stride < n) ? __ldg(b.gidx + j + k * stride) : 0u;
-        for (; j < n; j += U * stride)
-            {
-            double4 v[U];
-            unsigned int cur[U];
+            v[k] = ld256(b.vel + b.first + j + k * stride);
 #pragma unroll
-            for (int k = 0; k < U; k++)
-                {
-                cur[k] = nxt[k];
-                v[k] = make_double4(0.0, 0.0, 0.0, 0.0);
-                if (j + k * stride < n)
-                    v[k] = ld256(b.vel + cur[k]);
-                }
-#pragma unroll
-            for (int k = 0; k < U; k++)
-                {
-                const unsigned long long jn = j + (U + k) * stride;
-                nxt[k] = jn < n ? __ldg(b.gidx + jn) : 0u;
-                }
-#pragma unroll
-            for (int k = 0; k < U; k++)
-                ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z); // (+0 for the padding slots)
-            }
+        for (int k = 0; k < U; k++)
+            ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z);
         }
-    else
+    for (; j < n; j += stride)
         {
-        for (; j + (U - 1) * stride < n; j += U * stride)
-            {
-            double4 v[U];
-#pragma unroll
-            for (int k = 0; k < U; k++)
-                v[k] = ld256(b.vel + b.first + j + k * stride);
-#pragma unroll
-            for (int k = 0; k < U; k++)
-                ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z);
-            }
-        for (; j < n; j += stride)
-            {
-            const double4 v = ld256(b.vel + b.first + j);
-            ke[0] += v.w * (v.x * v.x + v.y * v.y + v.z * v.z);
-            }
+        const double4 v = ld256(b.vel + b.first + j);
+        ke[0] += v.w * (v.x * v.x + v.y * v.y + v.z * v.z);
         }
 #pragma unroll
     for (int k = 0; k < U; k++)
@@ -933,49 +952,58 @@ __device__ __forceinline__ void apply_force(const Final& fin, const ForceIn& f, 
         st256(f.force + i, force_of(i, __ldg(f.charge + i), fin, f));
     }
 
-template<int UNROLL>
-__device__ __forceinline__ void apply_rescale(double alpha, const BussiIn& b, const StreamGrid g = whole_grid())
+template<int UNROLL> __device__ __noinline__ void apply_rescale_list(double alpha, const BussiIn b, const StreamGrid g)
     {
+    // index list: indices fetched one iteration ahead (see reduce_ke_list)
     constexpr int U = UNROLL > 1 ? UNROLL : 1;
     const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
     unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     const unsigned long long n = b.n;
-    if (b.gidx)
+    unsigned int nxt[U];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+        nxt[k] = (j + k * stride < n) ? __ldg(b.gidx + j + k * stride) : 0u;
+    for (; j < n; j += U * stride)
         {
-        // index list: indices fetched one iteration ahead (see reduce_ke)
-        unsigned int nxt[U];
+        double4 v[U];
+        unsigned int cur[U];
 #pragma unroll
         for (int k = 0; k < U; k++)
-            nxt[k] = (j + k * stride < n) ? __ldg(b.gidx + j + k * stride) : 0u;
-        for (; j < n; j += U * stride)
             {
-            double4 v[U];
-            unsigned int cur[U];
-#pragma unroll
-            for (int k = 0; k < U; k++)
-                {
-                cur[k] = nxt[k];
-                if (j + k * stride < n)
-                    v[k] = ld256(b.vel + cur[k]);
-                }
-#pragma unroll
-            for (int k = 0; k < U; k++)
-                {
-                const unsigned long long jn = j + (U + k) * stride;
-                nxt[k] = jn < n ? __ldg(b.gidx + jn) : 0u;
-                }
-#pragma unroll
-            for (int k = 0; k < U; k++)
-                if (j + k * stride < n)
-                    {
-                    v[k].x = __dmul_rn(v[k].x, alpha);
-                    v[k].y = __dmul_rn(v[k].y, alpha);
-                    v[k].z = __dmul_rn(v[k].z, alpha);
-                    st256(b.vel + cur[k], v[k]);
-                    }
+            cur[k] = nxt[k];
+            if (j + k * stride < n)
+                v[k] = ld256(b.vel + cur[k]);
             }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            {
+            const unsigned long long jn = j + (U + k) * stride;
+            nxt[k] = jn < n ? __ldg(b.gidx + jn) : 0u;
+            }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            if (j + k * stride < n)
+                {
+                v[k].x = __dmul_rn(v[k].x, alpha);
+                v[k].y = __dmul_rn(v[k].y, alpha);
+                v[k].z = __dmul_rn(v[k].z, alpha);
+                st256(b.vel + cur[k], v[k]);
+                }
+        }
+    }
+
+template<int UNROLL>
+__device__ __forceinline__ void apply_rescale(double alpha, const BussiIn& b, const StreamGrid g = whole_grid())
+    {
+    constexpr int U = UNROLL > 1 ? UNROLL : 1;
+    if (b.gidx)
+        {
+        apply_rescale_list<UNROLL>(alpha, b, g);
         return;
         }
+    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
+    unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
+    const unsigned long long n = b.n;
     for (; j + (U - 1) * stride < n; j += U * stride)
         {
         double4 v[U];

@@ -127,3 +127,37 @@ def test_rhok_float32_positions(handle, N, T, K):
         assert np.abs((a[t, :, 0] + 1j * a[t, :, 1]) - ref).max() <= 1e-9 * N
     with pytest.raises(capi.CavbError):
         handle.rhok(d64, 13, 3 * N, N, T, d_k, K, r64)  # the internal float32 code is not a public stride
+
+
+@pytest.mark.parametrize("kmag", [3.0e4, 1.0e7, 1.0e12])
+def test_rhok_huge_arguments_take_the_library_path(handle, kmag):
+    """|k.r| >= 2^20 (and any inf / nan) leaves the inline two-constant Cody-Waite reduction for the library's
+    Payne-Hanek sincos (csrc/rhok.cu, `huge` branch) -- per particle, so a frame may mix both.  Against NumPy (libm does
+    an exact reduction as well): each term is exact to ~1 ulp of the ARGUMENT's rounding, |k.r| eps, on both sides, so
+    the sums agree to N |k.r|max eps."""
+    n_mol, K, T = 4000, 12, 2
+    s = synth.make_system(n_mol, replica=8)
+    frames = synth.random_walk_frames(s, T)
+    kvec = synth.fibonacci_sphere(K) * kmag
+    kr = np.abs(frames[0] @ kvec.T)
+    big = (kr >= 2.0 ** 20).mean()
+    assert big > 0.5 if kmag >= 1e7 else 0.0 < big < 1.0  # 3e4: a genuine mix of both branches
+    rho, _ = gpu_rhok(handle, frames, kvec, 3)
+    for t in range(T):
+        ref = O.numpy_density_field(frames[t], kvec)
+        # identical arguments on both sides (same FMA-free dot? no: the device contracts k.r to FMAs, NumPy's BLAS too,
+        # but not necessarily in the same order): allow the argument's own rounding, |k.r| * 2^-52, per term
+        tol = s.N * np.abs(frames[t] @ kvec.T).max() * 2.0 ** -52 * 4 + 1e-12
+        assert np.abs(rho[t] - ref).max() <= tol
+        assert np.all(np.abs(rho[t]) <= s.N)
+
+
+def test_rhok_nonfinite_positions_propagate(handle):
+    """inf / nan coordinates go through the library branch too and come out as nan, as in NumPy (cos(inf) = nan)."""
+    frames = np.zeros((1, 64, 3))
+    frames[0, 5, 0] = np.inf
+    kvec = synth.fibonacci_sphere(4) * 1.0
+    rho, _ = gpu_rhok(handle, frames, kvec, 3)
+    with np.errstate(invalid="ignore"):
+        ref = O.numpy_density_field(frames[0], kvec)
+    assert np.array_equal(np.isnan(rho[0].real), np.isnan(ref.real)) and np.isnan(rho[0].real).any()
