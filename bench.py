@@ -874,31 +874,48 @@ def run_b200(args):
     def e2e_val(sec):
         return world * N * e2e_steps / sec / 1e6
 
-    # raw PCIe rates of this box (pinned, 32 MB copies, one direction at a time and both together)
+    # raw PCIe rates of this box (pinned, 32 MB copies, one direction at a time and both together).  With N > 1 every
+    # rank measures AT THE SAME TIME (barrier before each measurement), so the figures are what a rank gets while the
+    # other ranks' copies load the same host memory and PCIe root complexes: the host-side limit of the e2e leg.
+    lib = capi.load()
+    nb = 32 * N
+    s2 = capi.Stream()
+
+    def rate(fn, reps=6):
+        fn()
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        capi.sync()
+        return nb * reps / (time.perf_counter() - t0) / 1e9
+
+    h2d = rate(lambda: lib.cavb200_memcpy_h2d(systems[0].pos.ptr, pin["pos"].ptr, nb, st))
+    d2h = rate(lambda: lib.cavb200_memcpy_d2h(pin_force.ptr, systems[0].force.ptr, nb, st))
+
+    def both():
+        lib.cavb200_memcpy_h2d(systems[0].pos.ptr, pin["pos"].ptr, nb, st)
+        lib.cavb200_memcpy_d2h(pin_force.ptr, systems[1].force.ptr, nb, s2.ptr)
+    duplex = 2 * rate(both)
+    rates = [(h2d, d2h, duplex)]
+    if cx.dist is not None:
+        rates = [None] * world
+        cx.dist.all_gather_object(rates, (h2d, d2h, duplex))
     pcie = None
     if rank == 0:
-        lib = capi.load()
-        nb = 32 * N
-        s2 = capi.Stream()
-        def rate(fn, reps=6):
-            fn()
-            capi.sync()
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                fn()
-            capi.sync()
-            return nb * reps / (time.perf_counter() - t0) / 1e9
-        h2d = rate(lambda: lib.cavb200_memcpy_h2d(systems[0].pos.ptr, pin["pos"].ptr, nb, st))
-        d2h = rate(lambda: lib.cavb200_memcpy_d2h(pin_force.ptr, systems[0].force.ptr, nb, st))
-        def both():
-            lib.cavb200_memcpy_h2d(systems[0].pos.ptr, pin["pos"].ptr, nb, st)
-            lib.cavb200_memcpy_d2h(pin_force.ptr, systems[1].force.ptr, nb, s2.ptr)
-        duplex = 2 * rate(both)
-        pcie = {"h2d_GBs": h2d, "d2h_GBs": d2h, "duplex_GBs": duplex,
-                "floor_ms_per_step": {"full_copy": max((52 * N + 32 * n_mol) / (h2d * 1e6), (32 * N + 32 * n_mol) / (d2h * 1e6)),
-                                      "headline": max((32 * N + 32 * n_mol) / (h2d * 1e6), (32 * N + 32 * n_mol) / (d2h * 1e6)),
-                                      "rank1_result": max((32 * N + 32 * n_mol) / (h2d * 1e6), 32 * n_mol / (d2h * 1e6))},
-                "note": "floor = the busier PCIe direction at this box's measured one-direction rate"}
+        a = np.array(rates)
+        h2d_r, d2h_r = float(a[:, 0].min()), float(a[:, 1].min())
+        pcie = {"h2d_GBs": h2d_r, "d2h_GBs": d2h_r, "duplex_GBs": float(a[:, 2].min()),
+                "floor_ms_per_step": {"full_copy": max((52 * N + 32 * n_mol) / (h2d_r * 1e6), (32 * N + 32 * n_mol) / (d2h_r * 1e6)),
+                                      "headline": max((32 * N + 32 * n_mol) / (h2d_r * 1e6), (32 * N + 32 * n_mol) / (d2h_r * 1e6)),
+                                      "rank1_result": max((32 * N + 32 * n_mol) / (h2d_r * 1e6), 32 * n_mol / (d2h_r * 1e6))},
+                "note": "floor = the busier PCIe direction at the measured one-direction rate"
+                        + (f"; {world} ranks copying concurrently: per-rank minimum shown, aggregate h2d {a[:, 0].sum():.0f} / d2h "
+                           f"{a[:, 1].sum():.0f} / duplex {a[:, 2].sum():.0f} GB/s over the host's memory and PCIe roots -- the "
+                           f"limiter of the e2e leg at this N (not a kernel or a collective)" if world > 1 else "")}
+        if world > 1:
+            pcie["per_rank_concurrent"] = {"h2d_GBs": [float(x) for x in a[:, 0]], "d2h_GBs": [float(x) for x in a[:, 1]],
+                                           "duplex_GBs": [float(x) for x in a[:, 2]]}
 
     assert h.fault_count == 0
 

@@ -94,6 +94,9 @@ int fill_bussi(BussiIn& b, double* vel, const uint32_t* gidx, uint32_t first, ui
     b.first = first;
     b.n = n;
     b.rescale = rescale;
+    // rescaled velocities first-to-evict when one system's arrays (116 B/particle) exceed half of the 126 MB L2
+    // (cavb200_internal.cuh st256_vel)
+    b.stream_st = (uint64_t)n * 116ull > (63ull << 20);
     b.kT = b.c = b.dof = b.r_normal = b.r_gamma = 0.0;
     b.half_kT = b.omc = b.gR2 = b.two_R = b.cdof = b.den = 0.0;
     if (a)

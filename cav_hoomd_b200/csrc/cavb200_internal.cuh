@@ -207,6 +207,51 @@ __device__ __forceinline__ void st256_stream(double4* p, const double4& v)
     asm volatile("st.global.L2::evict_first.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w)
                  : "memory");
     }
+// Rescaled velocities.  Measured (profiles/cache_policy_r2a.txt): marking these dirty lines first-to-evict lets the
+// write-back start early instead of competing with the next pass's reads -- 1M-particle step 30.9 -> 30.0 us, force +
+// Bussi 38.9 -> 37.6 us, 4M Bussi call 62.7 -> 58.3 us.  When several systems that together fit in L2 are cycled
+// through (262k particles x 4) it costs reuse instead (17.0 -> 18.3 us), so the launcher sets `ef` only when one
+// system's arrays alone exceed half of L2.  (evict_last, and default / .cs / evict_last for the force stores: slower.)
+__device__ __forceinline__ void st256_vel(double4* p, const double4& v, bool ef)
+    {
+    if (ef)
+        asm volatile("st.global.L2::evict_first.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w)
+                     : "memory");
+    else
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+    }
+// image flags: read once per call
+#ifndef CAVB_IMAGE_LD
+#define CAVB_IMAGE_LD 1 // 0: __ldg, 1: evict_first cache policy (force call 22.1 -> 21.6 us at 1M, profiles/cache_policy_r2a.txt)
+#endif
+__device__ __forceinline__ int ld_image(const int* p)
+    {
+#if CAVB_IMAGE_LD == 1
+    // (the L2::evict_first qualifier exists for 256-bit accesses only; narrower ones take a cache-policy operand)
+    int r;
+    asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n"
+                 "ld.global.nc.L2::cache_hint.s32 %0, [%1], pol; }" : "=r"(r) : "l"(p));
+    return r;
+#else
+    return __ldg(p);
+#endif
+    }
+// charges of the apply pass (their second and last use in a call)
+#ifndef CAVB_CHARGE2_LD
+#define CAVB_CHARGE2_LD 1 // 0: __ldg, 1: evict_first cache policy (profiles/cache_policy_r2a.txt)
+#endif
+__device__ __forceinline__ double ld_charge_last(const double* p)
+    {
+#if CAVB_CHARGE2_LD == 1
+    double r;
+    asm volatile("{ .reg .b64 pol; createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n"
+                 "ld.global.nc.L2::cache_hint.f64 %0, [%1], pol; }" : "=d"(r) : "l"(p));
+    return r;
+#else
+    return __ldg(p);
+#endif
+    }
+
 // programmatic dependent launch: wait for the previous kernel of the stream / let the next one start
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -300,6 +345,7 @@ struct BussiIn
     double cdof;     // c * dof
     double den;      // (1.0 - c) * (kT * dof / 2.0)
     int rescale;         // 0: KE only
+    int stream_st;       // rescaled velocities are stored first-to-evict (set by the launcher for systems larger than L2/2)
     };
 
 void fill_force_constants(ForceIn& f);

@@ -37,7 +37,8 @@ __device__ __forceinline__ void ring_end(unsigned long long* stamps, int mode, u
 // kernels
 // ------------------------------------------------------------------------------------------
 // variant 0, kernel 1: reduce; the last CTA to take a ticket combines and publishes Scalars + Final
-template<bool FORCE, bool BUSSI, int UNROLL, int LB>
+// (LIST: the thermostatted group is an index list -- Bussi-only instantiations, see hotpath.cuh reduce_ke)
+template<bool FORCE, bool BUSSI, int UNROLL, int LB, bool LIST>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_reduce(ForceIn f, BussiIn b, Partial* recs, Scalars* scalars, Final* fin_out, unsigned long long* ticket)
     {
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     pdl_wait();
     if (threadIdx.x == 0)
         sc.flags = 0u;
-    reduce_phase<FORCE, BUSSI, UNROLL>(f, b, sc);
+    reduce_phase<FORCE, BUSSI, UNROLL, LIST>(f, b, sc);
     pdl_launch_dependents();
     if (threadIdx.x == 0)
         {
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     }
 
 // variant 0, kernel 2
-template<bool FORCE, bool BUSSI, int UNROLL, int LB>
+template<bool FORCE, bool BUSSI, int UNROLL, int LB, bool LIST>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1) k_apply(ForceIn f, BussiIn b, const Final* fin_in)
     {
     __shared__ Final fin;
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1) k_apply(ForceIn f, Buss
     if (threadIdx.x == 0)
         fin = *fin_in;
     __syncthreads();
-    apply_phase<FORCE, BUSSI, UNROLL>(fin, f, b);
+    apply_phase<FORCE, BUSSI, UNROLL, LIST>(fin, f, b);
     }
 
 // variant 1: cooperative persistent kernel (co-residency guaranteed by cudaLaunchCooperativeKernel).
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1) k_apply(ForceIn f, Buss
 // by every CTA before it publishes anything and written back by CTA 0 after its combine -- i.e. after
 // every CTA has published, hence after every CTA has read it.  No host-side state, so the kernel is
 // safe under CUDA-graph replay and for any sequence of grid sizes.
-template<bool FORCE, bool BUSSI, int UNROLL, int LB, bool RING>
+template<bool FORCE, bool BUSSI, int UNROLL, int LB, bool RING, bool LIST>
 __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     k_fused(ForceIn f, BussiIn b, Partial* recs, Scalars* scalars, unsigned long long* epoch_ctr,
             unsigned long long* stamps)
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         if (stamp_mode == 2)
             ring_start(stamps, sc.epoch, t_start);
         }
-    reduce_phase<FORCE, BUSSI, UNROLL>(f, b, sc); // (its barriers also publish sc.epoch to the block)
+    reduce_phase<FORCE, BUSSI, UNROLL, LIST>(f, b, sc); // (its barriers also publish sc.epoch to the block)
     if (threadIdx.x == 0)
         publish_record(recs + blockIdx.x, sc.rec, sc.epoch);
     if (my_stamps)
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     constexpr bool PRE = !FORCE && BUSSI;
     // (only while the velocities still sit in L2 after the KE pass: 262k 7.24 -> 6.30 us, 1M 16.66 -> 16.03 us, but
     // 4M 63.1 -> 64.3 us, where the early loads go to HBM)
-    const bool pre = PRE && b.rescale && b.gidx == nullptr && b.first == 0 && b.n <= 2000000u;
+    const bool pre = PRE && !LIST && b.rescale && b.first == 0 && b.n <= 2000000u;
     VelPrefetch<PRE ? CAVB_FUSED_VEL_PREFETCH : 1> pv;
     if (pre)
         pv = prefetch_vel<PRE ? CAVB_FUSED_VEL_PREFETCH : 1>(b, whole_grid());
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
             rescale_prefetched<PRE ? CAVB_FUSED_VEL_PREFETCH : 1, UNROLL>(sc.fin.alpha, b, whole_grid(), pv);
         }
     else
-        apply_phase<FORCE, BUSSI, UNROLL>(sc.fin, f, b);
+        apply_phase<FORCE, BUSSI, UNROLL, LIST>(sc.fin, f, b);
     if (my_stamps)
         my_stamps[4] = globaltimer_ns();
     ring_end(stamps, stamp_mode, epoch);
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
         if (my_stamps)
             my_stamps[4] = globaltimer_ns();
         const FinalSectors preK = prefetch_final<false>(finals + 1);
-        const bool contiguous = b.gidx == nullptr && b.first == 0;
+        const bool contiguous = b.first == 0; // (the step takes a window of the index space, never a list)
         VelPrefetch<CAVB_VEL_PREFETCH> pv;
         if (contiguous)
             pv = prefetch_vel<CAVB_VEL_PREFETCH>(b, g);
@@ -415,9 +416,16 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
 // ------------------------------------------------------------------------------------------
 // LB = launch bound: 1024 caps the kernel at 64 registers/thread (two 512-thread CTAs or one
 // 1024-thread CTA per SM); 512 allows 128 registers for one 512-thread CTA per SM.
-template<bool FORCE, bool BUSSI, int UNROLL, int LB>
+template<bool FORCE, bool BUSSI, int UNROLL, int LB, bool LIST = false>
 static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaStream_t s)
     {
+    if (BUSSI && !LIST && b.gidx != nullptr)
+        {
+        // an index list: only the Bussi-only calls take one (cavb200_bussi, cavb200_bussi_ke)
+        if (FORCE)
+            return (int)cudaErrorInvalidValue;
+        return launch_t<FORCE, BUSSI && !FORCE, UNROLL, LB, !FORCE>(h, f, b, s);
+        }
     int threads = h->tune.threads;
     const unsigned long long work = (FORCE ? (unsigned long long)f.N : 0ull) > (BUSSI ? (unsigned long long)b.n : 0ull)
                                         ? (unsigned long long)f.N
@@ -544,7 +552,7 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         Scalars* sca = h->scalars;
         unsigned long long* ticket = h->counters + 4;
         void* a1[] = {&ff, &bb, &recs, &sca, &fin_dev, &ticket};
-        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_reduce<FORCE, BUSSI, UNROLL, LB>, a1));
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_reduce<FORCE, BUSSI, UNROLL, LB, LIST>, a1));
         h->launches += 1;
         return 0;
         }
@@ -553,7 +561,7 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         {
         int per_sm = 0;
         const bool ring = h->tune.stamps == 2;
-        CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<FORCE, BUSSI, UNROLL, LB, false>, threads, 0));
+        CAVB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<FORCE, BUSSI, UNROLL, LB, false, LIST>, threads, 0));
         if (per_sm < 1)
             return (int)cudaErrorLaunchOutOfResources;
         int resident = per_sm * h->num_sms;
@@ -591,8 +599,8 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
             }
         cfg.attrs = attrs;
         cfg.numAttrs = na;
-        CAVB_CHECK(cudaLaunchKernelExC(&cfg, ring ? (const void*)k_fused<FORCE, BUSSI, UNROLL, LB, true>
-                                                  : (const void*)k_fused<FORCE, BUSSI, UNROLL, LB, false>, args));
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, ring ? (const void*)k_fused<FORCE, BUSSI, UNROLL, LB, true, LIST>
+                                                  : (const void*)k_fused<FORCE, BUSSI, UNROLL, LB, false, LIST>, args));
         h->launches += 1;
         return 0;
         }
@@ -614,10 +622,10 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         Scalars* sca = h->scalars;
         unsigned long long* ticket = h->counters + 4;
         void* a1[] = {&ff, &bb, &recs, &sca, &fin_dev, &ticket};
-        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_reduce<FORCE, BUSSI, UNROLL, LB>, a1));
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_reduce<FORCE, BUSSI, UNROLL, LB, LIST>, a1));
         const Final* fin_c = fin_dev;
         void* a2[] = {&ff, &bb, &fin_c};
-        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_apply<FORCE, BUSSI, UNROLL, LB>, a2));
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_apply<FORCE, BUSSI, UNROLL, LB, LIST>, a2));
         }
     h->launches += 2;
     return 0;

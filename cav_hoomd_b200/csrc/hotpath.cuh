@@ -201,60 +201,15 @@ __device__ __forceinline__ StreamGrid whole_grid()
 // round trips per loop iteration as first written (18.0 vs 16.1 us per 1M-particle Bussi call, profiles/ab_r2b.txt).
 // The index loads are therefore software-pipelined one iteration ahead -- the indices of iteration i+1 are requested
 // together with the velocities of iteration i -- so only the first iteration pays the second round trip.
-// (The list paths are separate, non-inlined functions: inlined, their loops changed the register allocation of the
-// persistent kernels around them -- which sit exactly at their 80-register budget -- and cost the contiguous step
-// 0.3 us at 1M particles.  One call per kernel launch.)
-template<int UNROLL> __device__ __noinline__ double reduce_ke_list(const BussiIn b, const StreamGrid g)
+// (The list loops are compiled only into the kernel instantiations that take an index list -- template parameter LIST,
+// the Bussi-only kernels of cavb200_bussi / cavb200_bussi_ke.  Sharing one kernel with the window path changed the
+// register allocation of the persistent kernels around the loops, which sit exactly at their 80-register budget, and
+// cost the contiguous step 0.3 us at 1M particles; as non-inlined functions they miscompiled, nvcc 12.9: wrong alpha
+// from the second call on in tests/test_bussi_gpu.py::test_bussi_index_list_group_and_cumulative.)
+template<int UNROLL, bool LIST>
+__device__ __forceinline__ void reduce_ke(Acc& a, const BussiIn& b, const StreamGrid g = whole_grid())
     {
     constexpr int U = UNROLL > 1 ? UNROLL : 1;
-    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
-    unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
-    const unsigned long long n = b.n;
-    double ke[U];
-    unsigned int nxt[U];
-#pragma unroll
-    for (int k = 0; k < U; k++)
-        {
-        ke[k] = 0.0;
-        nxt[k] = (j + k * stride < n) ? __ldg(b.gidx + j + k * stride) : 0u;
-        }
-    for (; j < n; j += U * stride)
-        {
-        double4 v[U];
-        unsigned int cur[U];
-#pragma unroll
-        for (int k = 0; k < U; k++)
-            {
-            cur[k] = nxt[k];
-            v[k] = make_double4(0.0, 0.0, 0.0, 0.0);
-            if (j + k * stride < n)
-                v[k] = ld256(b.vel + cur[k]);
-            }
-#pragma unroll
-        for (int k = 0; k < U; k++)
-            {
-            const unsigned long long jn = j + (U + k) * stride;
-            nxt[k] = jn < n ? __ldg(b.gidx + jn) : 0u;
-            }
-#pragma unroll
-        for (int k = 0; k < U; k++)
-            ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z); // (+0 for the padding slots)
-        }
-    double sum = 0.0;
-#pragma unroll
-    for (int k = 0; k < U; k++)
-        sum += ke[k];
-    return sum;
-    }
-
-template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const BussiIn& b, const StreamGrid g = whole_grid())
-    {
-    constexpr int U = UNROLL > 1 ? UNROLL : 1;
-    if (b.gidx)
-        {
-        a.ke += reduce_ke_list<UNROLL>(b, g);
-        return;
-        }
     const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
     unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     const unsigned long long n = b.n;
@@ -262,20 +217,52 @@ template<int UNROLL> __device__ __forceinline__ void reduce_ke(Acc& a, const Bus
 #pragma unroll
     for (int k = 0; k < U; k++)
         ke[k] = 0.0;
-    for (; j + (U - 1) * stride < n; j += U * stride)
+    if (LIST)
         {
-        double4 v[U];
+        unsigned int nxt[U];
 #pragma unroll
         for (int k = 0; k < U; k++)
-            v[k] = ld256(b.vel + b.first + j + k * stride);
+            nxt[k] = (j + k * stride < n) ? __ldg(b.gidx + j + k * stride) : 0u;
+        for (; j < n; j += U * stride)
+            {
+            double4 v[U];
+            unsigned int cur[U];
 #pragma unroll
-        for (int k = 0; k < U; k++)
-            ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z);
+            for (int k = 0; k < U; k++)
+                {
+                cur[k] = nxt[k];
+                v[k] = make_double4(0.0, 0.0, 0.0, 0.0);
+                if (j + k * stride < n)
+                    v[k] = ld256(b.vel + cur[k]);
+                }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                {
+                const unsigned long long jn = j + (U + k) * stride;
+                nxt[k] = jn < n ? __ldg(b.gidx + jn) : 0u;
+                }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z); // (+0 for the padding slots)
+            }
         }
-    for (; j < n; j += stride)
+    else
         {
-        const double4 v = ld256(b.vel + b.first + j);
-        ke[0] += v.w * (v.x * v.x + v.y * v.y + v.z * v.z);
+        for (; j + (U - 1) * stride < n; j += U * stride)
+            {
+            double4 v[U];
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                v[k] = ld256(b.vel + b.first + j + k * stride);
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                ke[k] += v[k].w * (v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z);
+            }
+        for (; j < n; j += stride)
+            {
+            const double4 v = ld256(b.vel + b.first + j);
+            ke[0] += v.w * (v.x * v.x + v.y * v.y + v.z * v.z);
+            }
         }
 #pragma unroll
     for (int k = 0; k < U; k++)
@@ -315,9 +302,9 @@ __device__ __forceinline__ void reduce_stream(Acc& a, const ForceIn& f, const Bu
                 {
                 p[k] = ld256_stream(f.pos + j);
                 c[k] = __ldg(f.charge + j);
-                ix[k] = __ldg(f.image + 3 * j + 0);
-                iy[k] = __ldg(f.image + 3 * j + 1);
-                iz[k] = __ldg(f.image + 3 * j + 2);
+                ix[k] = ld_image(f.image + 3 * j + 0);
+                iy[k] = ld_image(f.image + 3 * j + 1);
+                iz[k] = ld_image(f.image + 3 * j + 2);
                 }
             if (KE)
                 v[k] = ld256_na(b.vel + j);
@@ -338,9 +325,9 @@ __device__ __forceinline__ void reduce_stream(Acc& a, const ForceIn& f, const Bu
             {
             const double4 p = ld256_stream(f.pos + i);
             const double c = __ldg(f.charge + i);
-            const int ix = __ldg(f.image + 3 * i + 0);
-            const int iy = __ldg(f.image + 3 * i + 1);
-            const int iz = __ldg(f.image + 3 * i + 2);
+            const int ix = ld_image(f.image + 3 * i + 0);
+            const int iy = ld_image(f.image + 3 * i + 1);
+            const int iz = ld_image(f.image + 3 * i + 2);
             take_particle(a, (unsigned int)i, p, c, ix, iy, iz, f);
             }
         if (KE && i < nk)
@@ -429,28 +416,28 @@ __device__ __forceinline__ void block_merge(Acc& a, const ForceIn& f, BlockScrat
     __syncthreads();
     }
 
-template<bool FORCE, bool BUSSI, int UNROLL>
+template<bool FORCE, bool BUSSI, int UNROLL, bool LIST = false>
 __device__ __forceinline__ void reduce_loops(Acc& a, const ForceIn& f, const BussiIn& b, const StreamGrid g = whole_grid())
     {
     acc_zero(a);
-    if (BUSSI && (b.gidx != nullptr || b.first != 0))
+    if (BUSSI && (LIST || b.first != 0))
         {
         // index-list group or a group that does not start at particle 0: the velocity pass cannot
         // share the particle loop
         if (FORCE)
             reduce_stream<true, false, UNROLL>(a, f, b, g);
-        reduce_ke<UNROLL>(a, b, g);
+        reduce_ke<UNROLL, LIST>(a, b, g);
         }
     else
         reduce_stream<FORCE, BUSSI, UNROLL>(a, f, b, g);
     }
 
-template<bool FORCE, bool BUSSI, int UNROLL>
+template<bool FORCE, bool BUSSI, int UNROLL, bool LIST = false>
 __device__ __forceinline__ void reduce_phase(const ForceIn& f, const BussiIn& b, BlockScratch& sc,
                                              const StreamGrid g = whole_grid())
     {
     Acc a;
-    reduce_loops<FORCE, BUSSI, UNROLL>(a, f, b, g);
+    reduce_loops<FORCE, BUSSI, UNROLL, LIST>(a, f, b, g);
     block_merge<FORCE, BUSSI>(a, f, sc);
     }
 
@@ -491,6 +478,7 @@ __device__ __forceinline__ void publish_record(Partial* dst, const Partial& src,
 #define CAVB_FINAL_POLL_NS 300
 #endif
 template<bool SYS> __device__ __forceinline__ double4 ld_rec(const double4* p) { return SYS ? ld256_sys(p) : ld256_cg(p); }
+// (Looking at the timeout clock only every 16th or 256th poll was measured: force call 22.1 -> 22.5 us, no gain elsewhere.)
 template<bool WAIT, bool SYS = false, int POLL_NS = CAVB_POLL_NS>
 __device__ __forceinline__ double4 read_sector(const double4* p, unsigned long long epoch, bool& late)
     {
@@ -575,6 +563,9 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
     {
     const unsigned int tid = threadIdx.x;
     const unsigned int lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
+    // (Measured, profiles/fold_threads_r2a.txt: letting a thread take two or more records so that fewer warps run the
+    // compensated tree -- 5, 3 or 2 warps instead of 10 -- makes the force call SLOWER, 22.2 -> 23.1 / 23.7 / 24.2 us:
+    // the fold is bound by the chain of round trips per thread, not by FP64 throughput.)
     const unsigned int work_warps = min(nwarps, (unsigned int)((G + 31) >> 5));
     bool late = false;
 
@@ -952,80 +943,73 @@ __device__ __forceinline__ void apply_force(const Final& fin, const ForceIn& f, 
         st256(f.force + i, force_of(i, __ldg(f.charge + i), fin, f));
     }
 
-template<int UNROLL> __device__ __noinline__ void apply_rescale_list(double alpha, const BussiIn b, const StreamGrid g)
+template<int UNROLL, bool LIST>
+__device__ __forceinline__ void apply_rescale(double alpha, const BussiIn& b, const StreamGrid g = whole_grid())
     {
-    // index list: indices fetched one iteration ahead (see reduce_ke_list)
     constexpr int U = UNROLL > 1 ? UNROLL : 1;
     const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
     unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
     const unsigned long long n = b.n;
-    unsigned int nxt[U];
-#pragma unroll
-    for (int k = 0; k < U; k++)
-        nxt[k] = (j + k * stride < n) ? __ldg(b.gidx + j + k * stride) : 0u;
-    for (; j < n; j += U * stride)
+    if (LIST)
         {
-        double4 v[U];
-        unsigned int cur[U];
+        // index list: indices fetched one iteration ahead (see reduce_ke)
+        unsigned int nxt[U];
 #pragma unroll
         for (int k = 0; k < U; k++)
+            nxt[k] = (j + k * stride < n) ? __ldg(b.gidx + j + k * stride) : 0u;
+        for (; j < n; j += U * stride)
             {
-            cur[k] = nxt[k];
-            if (j + k * stride < n)
-                v[k] = ld256(b.vel + cur[k]);
-            }
+            double4 v[U];
+            unsigned int cur[U];
 #pragma unroll
-        for (int k = 0; k < U; k++)
+            for (int k = 0; k < U; k++)
+                {
+                cur[k] = nxt[k];
+                if (j + k * stride < n)
+                    v[k] = ld256(b.vel + cur[k]);
+                }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                {
+                const unsigned long long jn = j + (U + k) * stride;
+                nxt[k] = jn < n ? __ldg(b.gidx + jn) : 0u;
+                }
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                if (j + k * stride < n)
+                    {
+                    v[k].x = __dmul_rn(v[k].x, alpha);
+                    v[k].y = __dmul_rn(v[k].y, alpha);
+                    v[k].z = __dmul_rn(v[k].z, alpha);
+                    st256_vel(b.vel + cur[k], v[k], b.stream_st != 0);
+                    }
+            }
+        }
+    else
+        {
+        for (; j + (U - 1) * stride < n; j += U * stride)
             {
-            const unsigned long long jn = j + (U + k) * stride;
-            nxt[k] = jn < n ? __ldg(b.gidx + jn) : 0u;
-            }
+            double4 v[U];
 #pragma unroll
-        for (int k = 0; k < U; k++)
-            if (j + k * stride < n)
+            for (int k = 0; k < U; k++)
+                v[k] = ld256(b.vel + b.first + j + k * stride);
+#pragma unroll
+            for (int k = 0; k < U; k++)
                 {
                 v[k].x = __dmul_rn(v[k].x, alpha);
                 v[k].y = __dmul_rn(v[k].y, alpha);
                 v[k].z = __dmul_rn(v[k].z, alpha);
-                st256(b.vel + cur[k], v[k]);
+                st256_vel(b.vel + b.first + j + k * stride, v[k], b.stream_st != 0);
                 }
-        }
-    }
-
-template<int UNROLL>
-__device__ __forceinline__ void apply_rescale(double alpha, const BussiIn& b, const StreamGrid g = whole_grid())
-    {
-    constexpr int U = UNROLL > 1 ? UNROLL : 1;
-    if (b.gidx)
-        {
-        apply_rescale_list<UNROLL>(alpha, b, g);
-        return;
-        }
-    const unsigned long long stride = (unsigned long long)g.nblk * blockDim.x;
-    unsigned long long j = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
-    const unsigned long long n = b.n;
-    for (; j + (U - 1) * stride < n; j += U * stride)
-        {
-        double4 v[U];
-#pragma unroll
-        for (int k = 0; k < U; k++)
-            v[k] = ld256(b.vel + b.first + j + k * stride);
-#pragma unroll
-        for (int k = 0; k < U; k++)
-            {
-            v[k].x = __dmul_rn(v[k].x, alpha);
-            v[k].y = __dmul_rn(v[k].y, alpha);
-            v[k].z = __dmul_rn(v[k].z, alpha);
-            st256(b.vel + b.first + j + k * stride, v[k]);
             }
-        }
-    for (; j < n; j += stride)
-        {
-        double4 v = ld256(b.vel + b.first + j);
-        v.x = __dmul_rn(v.x, alpha);
-        v.y = __dmul_rn(v.y, alpha);
-        v.z = __dmul_rn(v.z, alpha);
-        st256(b.vel + b.first + j, v);
+        for (; j < n; j += stride)
+            {
+            double4 v = ld256(b.vel + b.first + j);
+            v.x = __dmul_rn(v.x, alpha);
+            v.y = __dmul_rn(v.y, alpha);
+            v.z = __dmul_rn(v.z, alpha);
+            st256_vel(b.vel + b.first + j, v, b.stream_st != 0);
+            }
         }
     }
 
@@ -1049,7 +1033,7 @@ __device__ __forceinline__ void apply_stream(const Final& fin, const ForceIn& f,
         for (int k = 0; k < U; k++)
             {
             if (FORCE)
-                c[k] = __ldg(f.charge + i + k * stride);
+                c[k] = ld_charge_last(f.charge + i + k * stride);
             if (RESCALE)
                 v[k] = ld256(b.vel + i + k * stride);
             }
@@ -1064,38 +1048,38 @@ __device__ __forceinline__ void apply_stream(const Final& fin, const ForceIn& f,
                 v[k].x = __dmul_rn(v[k].x, alpha);
                 v[k].y = __dmul_rn(v[k].y, alpha);
                 v[k].z = __dmul_rn(v[k].z, alpha);
-                st256(b.vel + j, v[k]);
+                st256_vel(b.vel + j, v[k], b.stream_st != 0);
                 }
             }
         }
     for (; i < all; i += stride)
         {
         if (FORCE && i < nf)
-            st256_stream(f.force + i, force_of(i, __ldg(f.charge + i), fin, f));
+            st256_stream(f.force + i, force_of(i, ld_charge_last(f.charge + i), fin, f));
         if (RESCALE && i < nk)
             {
             double4 v = ld256(b.vel + i);
             v.x = __dmul_rn(v.x, alpha);
             v.y = __dmul_rn(v.y, alpha);
             v.z = __dmul_rn(v.z, alpha);
-            st256(b.vel + i, v);
+            st256_vel(b.vel + i, v, b.stream_st != 0);
             }
         }
     }
 
-template<bool FORCE, bool BUSSI, int UNROLL>
+template<bool FORCE, bool BUSSI, int UNROLL, bool LIST = false>
 __device__ __forceinline__ void apply_phase(const Final& fin, const ForceIn& f, const BussiIn& b,
                                             const StreamGrid g = whole_grid())
     {
     const bool rescale = BUSSI && b.rescale && fin.bussi_ok && fin.alpha != 1.0;
-    if (BUSSI && rescale && b.gidx == nullptr && b.first == 0)
+    if (BUSSI && rescale && !LIST && b.first == 0)
         apply_stream<FORCE, true, UNROLL>(fin, f, b, g);
     else
         {
         if (FORCE)
             apply_stream<true, false, UNROLL>(fin, f, b, g);
         if (BUSSI && rescale)
-            apply_rescale<UNROLL>(fin.alpha, b, g);
+            apply_rescale<UNROLL, LIST>(fin.alpha, b, g);
         }
     }
 
@@ -1136,7 +1120,7 @@ __device__ __forceinline__ void rescale_prefetched(double alpha, const BussiIn& 
             v.x = __dmul_rn(v.x, alpha);
             v.y = __dmul_rn(v.y, alpha);
             v.z = __dmul_rn(v.z, alpha);
-            st256(b.vel + i + k * stride, v);
+            st256_vel(b.vel + i + k * stride, v, b.stream_st != 0);
             }
         }
     i += (unsigned long long)PRE * stride;
@@ -1152,7 +1136,7 @@ __device__ __forceinline__ void rescale_prefetched(double alpha, const BussiIn& 
             v[k].x = __dmul_rn(v[k].x, alpha);
             v[k].y = __dmul_rn(v[k].y, alpha);
             v[k].z = __dmul_rn(v[k].z, alpha);
-            st256(b.vel + i + k * stride, v[k]);
+            st256_vel(b.vel + i + k * stride, v[k], b.stream_st != 0);
             }
         }
     for (; i < n; i += stride)
@@ -1161,7 +1145,7 @@ __device__ __forceinline__ void rescale_prefetched(double alpha, const BussiIn& 
         v.x = __dmul_rn(v.x, alpha);
         v.y = __dmul_rn(v.y, alpha);
         v.z = __dmul_rn(v.z, alpha);
-        st256(b.vel + i, v);
+        st256_vel(b.vel + i, v, b.stream_st != 0);
         }
     }
 
@@ -1179,7 +1163,7 @@ template<int PRE> __device__ __forceinline__ ChargePrefetch<PRE> prefetch_charge
     const unsigned long long i0 = (unsigned long long)g.blk * blockDim.x + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < PRE; k++)
-        p.c[k] = (i0 + k * stride < (unsigned long long)f.N) ? __ldg(f.charge + i0 + k * stride) : 0.0;
+        p.c[k] = (i0 + k * stride < (unsigned long long)f.N) ? ld_charge_last(f.charge + i0 + k * stride) : 0.0;
     return p;
     }
 template<int PRE, int U>
@@ -1199,13 +1183,13 @@ __device__ __forceinline__ void forces_prefetched(const Final& fin, const ForceI
         double c[U];
 #pragma unroll
         for (int k = 0; k < U; k++)
-            c[k] = __ldg(f.charge + i + k * stride);
+            c[k] = ld_charge_last(f.charge + i + k * stride);
 #pragma unroll
         for (int k = 0; k < U; k++)
             st256_stream(f.force + i + k * stride, force_of(i + k * stride, c[k], fin, f));
         }
     for (; i < N; i += stride)
-        st256_stream(f.force + i, force_of(i, __ldg(f.charge + i), fin, f));
+        st256_stream(f.force + i, force_of(i, ld_charge_last(f.charge + i), fin, f));
     }
 
 

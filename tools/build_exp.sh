@@ -13,3 +13,4 @@ done
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/exp/libcavb200_$NAME.so build/exp/$NAME/*.o -ldl
 echo built build/exp/libcavb200_$NAME.so
+rm -rf build/exp/$NAME
