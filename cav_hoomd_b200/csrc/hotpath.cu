@@ -430,14 +430,16 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
     const unsigned long long work = (FORCE ? (unsigned long long)f.N : 0ull) > (BUSSI ? (unsigned long long)b.n : 0ull)
                                         ? (unsigned long long)f.N
                                         : (unsigned long long)b.n;
-    if (FORCE && BUSSI && UNROLL == 2 && LB == 384 && threads == 384 && h->tune.auto_threads && h->tune.ctas_per_sm == 2)
+    // (the Bussi-only call follows the same rule -- 1M: 15.9 us at 384 threads, 15.6 at 352, profiles/threads_r2a.txt;
+    // the force-only call is flat in the CTA size)
+    if (BUSSI && UNROLL == 2 && LB == 384 && threads == 384 && h->tune.auto_threads && h->tune.ctas_per_sm == 2)
         {
         // Step kernel, default shape: a thread walks ceil(q) particles (q = work / streaming threads) two at a time, so
         // each of its four passes is ceil(ceil(q) / 2) dependent memory round trips.  Among 320 / 352 / 384 threads per
         // CTA take the fewest round trips, and on a tie the fewest threads (measured, tools/threads_sweep.py,
         // profiles/threads_r1a.txt: 1M particles 31.09 us at 384 -> 30.57 us at 352; 2M and more stay at 384; 262k and
         // 500k go to 320).
-        const unsigned long long ctas = (unsigned long long)h->num_sms * 2 - (h->tune.variant == 3 ? 1 : 0);
+        const unsigned long long ctas = (unsigned long long)h->num_sms * 2 - ((FORCE && h->tune.variant == 3) ? 1 : 0);
         unsigned long long best_rounds = ~0ull;
         for (int t = 320; t <= 384; t += 32)
             {
