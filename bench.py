@@ -103,7 +103,18 @@ class NumaLocal:
                     cpus.update(range(int(lo), int(hi or lo) + 1))
                 self._cpus = cpus & os.sched_getaffinity(0)
             else:
+                # sysfs reports no node (the case in this pool's containers): ask NVML for the CPUs closest to the GPU
                 self._cpus = set()
+                try:
+                    ncpu = os.cpu_count() or 1
+                    words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx), (ncpu + 63) // 64)
+                    near = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+                    near &= os.sched_getaffinity(0)
+                    if near and len(near) < len(os.sched_getaffinity(0)):
+                        self._cpus = near
+                        self.info["nvml_cpu_affinity"] = f"{len(near)} of {len(os.sched_getaffinity(0))} cpus"
+                except Exception:
+                    pass
         except Exception:
             self._cpus = set()
 
