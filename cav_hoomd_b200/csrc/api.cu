@@ -171,6 +171,7 @@ int cavb200_create(cavb200_handle** out, int device)
     h->tune.unroll = 2;
     h->tune.pdl = 1;
     h->tune.auto_threads = 1;
+    h->tune.small_n = 1024;
     h->shard.mode = 0;
     h->shard.nranks = 1;
     *out = h;
@@ -218,6 +219,7 @@ static int* tuning_slot(cavb::Tuning* t, const char* key)
     if (!strcmp(key, "ke_first")) return &t->ke_first;
     if (!strcmp(key, "auto_threads")) return &t->auto_threads;
     if (!strcmp(key, "md_shape")) return &t->md_shape;
+    if (!strcmp(key, "small_n")) return &t->small_n;
     return nullptr;
     }
 

@@ -93,6 +93,7 @@ struct Tuning
     int md_shape;        // cavb200_md_step_fused launch shape: 0 = one 768-thread CTA per SM (default), 1 = two 384-thread CTAs
     int auto_threads;    // step kernel: pick 320 / 352 / 384 threads per CTA from the particle count (1) or use `threads` (0)
     int ke_first;        // folder step kernel: thermostat half first (1) or dipole half first (0)
+    int small_n;         // calls over at most this many particles run as ONE CTA with no inter-CTA hand-off (0: off)
     };
 
 struct ShardState

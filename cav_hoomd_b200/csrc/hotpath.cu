@@ -411,6 +411,36 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     ring_end(stamps, stamp_mode, epoch);
     }
 
+// Small systems (tuning "small_n", default 1024 particles; the reference's own example runs 501): ONE CTA does the whole
+// call -- reduce, block merge, finalize, apply -- so there is no hand-off between CTAs at all.  At 501 particles the
+// two-CTA persistent kernels take 5.5 / 3.7 / 8.7 us (force / Bussi / step), nearly all of it the global-memory hand-off;
+// this one takes 3.8 / 3.3 / 6.2 us and is bound by its chain of latencies (profiles/small_n_r2a.txt: it wins below ~1000
+// particles).  Same per-thread orders and the same merge trees for the step as for the two calls, so cavb200_step stays
+// bit-identical to cavb200_force + cavb200_bussi.
+template<bool FORCE, bool BUSSI, bool LIST>
+__global__ void __launch_bounds__(1024, 1) k_small(ForceIn f, BussiIn b, Scalars* scalars, Final* fin_out)
+    {
+    __shared__ BlockScratch sc;
+    pdl_wait();
+    if (threadIdx.x == 0)
+        sc.flags = 0u;
+    StreamGrid g;
+    g.nblk = 1;
+    g.blk = 0;
+    reduce_phase<FORCE, BUSSI, 2, LIST>(f, b, sc, g);
+    if (threadIdx.x == 0)
+        {
+        finalize<FORCE, BUSSI>(f, b, sc, scalars, true);
+        if (FORCE && !BUSSI && f.force == nullptr)
+            *fin_out = sc.fin; // rank-1 mode: the consumers read Dq / F_L from here
+        }
+    __syncthreads();
+    pdl_launch_dependents();
+    if (FORCE && !BUSSI && f.force == nullptr)
+        return;
+    apply_phase<FORCE, BUSSI, 2, LIST>(sc.fin, f, b, g);
+    }
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -425,6 +455,34 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         if (FORCE)
             return (int)cudaErrorInvalidValue;
         return launch_t<FORCE, BUSSI && !FORCE, UNROLL, LB, !FORCE>(h, f, b, s);
+        }
+        {
+        const unsigned long long work_small = (FORCE ? (unsigned long long)f.N : 0ull) > (BUSSI ? (unsigned long long)b.n : 0ull)
+                                                  ? (unsigned long long)f.N
+                                                  : (unsigned long long)b.n;
+        if (h->tune.small_n > 0 && work_small <= (unsigned long long)h->tune.small_n)
+            {
+            // one CTA, as many threads as there are particles (rounded up to a warp, at most 1024)
+            int t = (int)((work_small + 31) / 32 * 32);
+            t = t < 64 ? 64 : (t > 1024 ? 1024 : t);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(1);
+            cfg.blockDim = dim3(t);
+            cfg.stream = s;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr.val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = h->tune.pdl ? 1 : 0;
+            ForceIn ff = f;
+            BussiIn bb = b;
+            Scalars* sca = h->scalars;
+            Final* fo = const_cast<Final*>(rank1_final(h));
+            void* args[] = {&ff, &bb, &sca, &fo};
+            CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_small<FORCE, BUSSI, LIST>, args));
+            h->launches += 1;
+            return 0;
+            }
         }
     int threads = h->tune.threads;
     const unsigned long long work = (FORCE ? (unsigned long long)f.N : 0ull) > (BUSSI ? (unsigned long long)b.n : 0ull)

@@ -293,3 +293,52 @@ def test_step_randomised_cases(coracle):
             assert out[5]["err"] == 0.0 or n == 0, (case, n_mol, photon, first, n)
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("photon", ["last", "first", "middle", "absent", "duplicated"])
+@pytest.mark.parametrize("n_mol", [1, 2, 33, 385, 500, 799])
+def test_single_cta_kernel_for_small_systems(coracle, n_mol, photon):
+    """Calls over at most `small_n` particles (default 1024; the reference's own example has 501) run as ONE CTA without
+    any inter-CTA hand-off (k_small).  Same results as the multi-CTA persistent kernels (tuning small_n = 0) -- the dipole
+    to the last bit or two (another partition of the same compensated sum), everything else 1e-14 -- both against the
+    oracle; the one-launch step stays bit-identical to the two calls; index-list and windowed groups included."""
+    h = capi.Handle(0)
+    try:
+        s = synth.make_system(n_mol, replica=n_mol, photon=photon)
+        first, n = (0, n_mol) if photon in ("last", "absent") else (0, s.N)
+        a = args_for(n)
+        outs = {}
+        for small in (0, 800):
+            h.set_tuning(small_n=small)
+            outs[small] = run_step(h, s, first, n, a)
+            check_against_oracle(coracle, s, first, n, a, outs[small])
+        f0, v0, en0, dip0, ph0, bo0 = outs[0]
+        f1, v1, en1, dip1, ph1, bo1 = outs[800]
+        assert ph0 == ph1 and np.abs(f1 - f0).max() <= 1e-14 * max(np.abs(f0).max(), 1e-300)
+        assert np.allclose(v1, v0, rtol=1e-14, atol=0) and abs(bo1["alpha"] - bo0["alpha"]) <= 1e-14
+        # the step == the two calls, bit for bit, on the single-CTA path too
+        h.set_tuning(small_n=800)
+        p = capi.Params.make(0.01, 1e-3)
+        dev = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+        d_f = capi.DeviceArray.from_numpy(np.full((s.N, 4), np.nan))
+        h.bussi_reset()
+        h.force(dev["pos"], dev["charge"], dev["image"], d_f, s.N, s.box, s.L_typeid, p)
+        h.bussi(dev["vel"], None, first, n, a)
+        assert np.array_equal(d_f.numpy().view(np.uint64), f1.view(np.uint64))
+        assert np.array_equal(dev["vel"].numpy().view(np.uint64), v1.view(np.uint64))
+        assert h.bussi_read()["alpha"] == bo1["alpha"] and np.array_equal(h.force_read()[0], en1)
+        # the group as an index list (the molecular particles), and the kinetic energy alone
+        idx = synth.molecular_group(s)
+        if len(idx):
+            d_idx = capi.DeviceArray.from_numpy(idx)
+            d_v = capi.DeviceArray.from_numpy(s.vel)
+            al = args_for(len(idx))
+            vref = s.vel.copy()
+            alpha_ref, ke_ref = coracle.bussi_step(vref, idx, al.dof, DT, KT, TAU, al.r_normal, al.gamma_draw, np.zeros(2))
+            h.bussi_ke(d_v, d_idx, 0, len(idx))
+            assert abs(h.bussi_read()["ke"] - ke_ref) <= 1e-12 * ke_ref
+            h.bussi(d_v, d_idx, 0, len(idx), al)
+            assert abs(h.bussi_read()["alpha"] - alpha_ref) <= 1e-12 * abs(alpha_ref)
+            assert np.allclose(d_v.numpy(), vref, rtol=1e-12, atol=0)
+    finally:
+        h.close()
