@@ -471,6 +471,8 @@ __device__ __forceinline__ void publish_record(Partial* dst, const Partial& src,
 // whole-grid folds (k_fused, k_split) want it short -- 64 -> 16 ns: Bussi call 17.7 -> 16.7 us, force call
 // 23.6 -> 23.35 us (0 ns is no better); the streaming CTAs of k_split_folder waiting for a Final record want it
 // long -- every warp of the grid polls the same sector: 0 / 64 / 300 ns give 31.88 / 31.87 / 31.63 us per step.
+// (Round 2, with the L2 policies of profiles/cache_policy_r2a.txt: 100 / 300 / 600 ns give 29.91 / 29.85 / 29.84 us; letting
+// ONE warp per CTA poll Final(K) with a 16 or 64 ns sleep and hand alpha on through shared memory: 30.02 us.)
 #ifndef CAVB_POLL_NS
 #define CAVB_POLL_NS 16
 #endif

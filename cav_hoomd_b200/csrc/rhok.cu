@@ -323,7 +323,10 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
         target = h->rhok_partials;
         }
     // wave vectors in slabs of at most threads*KB = 1024 (one launch for the usual K); KB = 4 k per thread
-    constexpr int KB = 4;
+#ifndef RHOK_KB
+#define RHOK_KB 4
+#endif
+    constexpr int KB = RHOK_KB;
     for (uint32_t k0 = 0; k0 < K; k0 += (uint32_t)threads * KB)
         {
         const uint32_t Ks = (K - k0) < (uint32_t)threads * KB ? (K - k0) : (uint32_t)threads * KB;
