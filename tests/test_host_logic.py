@@ -1,5 +1,7 @@
 """Host-side logic (no GPU): synthetic inputs, replica parsing, shard partitioning, RNG keying,
 the API surface of the host mirrors."""
+import os
+
 import numpy as np
 import pytest
 
@@ -88,3 +90,35 @@ def test_host_mirror_api_surface():
     t = BussiReservoir(kT=1.5, tau=0.1)
     assert t.kT == 1.5 and t.tau == 0.1 and t.total_reservoir_energy == 0.0  # reference test :59-61
     t.reset_reservoir_energy()  # no-op when not attached (reference thermostats.py:137-158)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_bench_sharded_blocks_tile_the_16m_box(world):
+    """bench.py's `sharded` leg (BASELINE configs[3]) gives rank r the block shard_bounds(16 000 001, world)[r]; the
+    blocks must tile the index space in rank order with 32-particle-aligned starts, and the photon (globally last) must
+    fall into the last non-empty block, whose thermostatted window then excludes exactly that particle."""
+    from cav_hoomd_b200 import shard
+    N = 16_000_001
+    b = shard.shard_bounds(N, world)
+    assert b[0][0] == 0 and b[-1][1] == N and all(lo % 32 == 0 for lo, _ in b)
+    assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+    sizes = [hi - lo for lo, hi in b]
+    assert max(sizes) - min(sizes) <= 32 * world + 1 and min(sizes) > 0
+    last = world - 1
+    assert b[last][0] <= N - 1 < b[last][1]
+    # what the leg computes per rank: molecular particles of the block, the window [0, n_loc_mol)
+    n_loc_mol = [(hi - lo) - (1 if r == last else 0) for r, (lo, hi) in enumerate(b)]
+    assert sum(n_loc_mol) == N - 1
+
+
+def test_bench_config_is_identical_on_both_arms():
+    """The driver compares the `config` dictionaries of the two arms: both come from bench.bench_config."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c1, c8 = bench.bench_config(1_000_000, 1), bench.bench_config(1_000_000, 8)
+    assert set(c1) == {"workload", "l2"} and "BASELINE configs[1]" in c1["workload"]
+    assert "8 independent replicas" in c8["workload"] and c1["l2"] == c8["l2"]
+    assert bench.bench_config(1_000_000, 1) == c1
