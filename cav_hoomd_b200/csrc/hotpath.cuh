@@ -51,6 +51,7 @@ struct __align__(32) BlockScratch
     double red[8][32]; // [component][warp]: conflict-free when lane == warp index
     unsigned long long red_ull[32];
     unsigned int red_cnt[32]; // per-warp count of records holding an 'L' candidate (bit 31: multi flag)
+    unsigned int red_nl[32];  // per-warp number of 'L' particles
     double wq[32][3];         // per-warp: q of the warp's best candidate
     double wt[32][3];         // per-warp: its dipole term (kept only by rank-level merges)
     unsigned int min_cand;
@@ -81,70 +82,156 @@ __device__ __forceinline__ void acc_zero(Acc& a)
     a.n_L = 0;
     }
 
-// (Measured: the whole-grid fold of k_fused takes 4.25 us the first time through and 2.25 us when it is run a
-// second time in the same launch; rolling this level loop to shrink the code -- 5664 -> 3208 instructions --
+// The trees.  A thread's Acc holds four (hi, lo) pairs worth summing -- d.x, d.y, d.z and (KE, nothing) -- and a
+// butterfly over all four costs 20 pair additions and 40 64-bit shuffles per warp, every lane computing every total.
+// With 24 warps of an SM arriving at the end of the reduce together that is ~3000 DADD and ~2000 SHFL warp instructions
+// queued on two pipes: measured 0.8 us of the 21.6 us force call for the z component alone (profiles/tree4_r2a.txt).
+// So the tree is TRANSPOSED: after the first exchange (lanes l and l^16) a lane carries on with two of the four pairs,
+// after the second (l^8) with one, and lanes 8s..8s+7 end up holding the warp's total of pair s (Slot): 6 pair additions
+// and 12 shuffles.  The pairings (16, 8, 4, 2, 1) are the butterfly's, so the plain-double KE -- the hi word of pair 3,
+// whose lo word is ignored -- keeps the bits of a plain butterfly sum, which is what the Bussi-only kernels use.
+// (Measured before: the whole-grid fold of k_fused takes 4.25 us the first time through and 2.25 us when it is run a
+// second time in the same launch; rolling the level loop to shrink the code -- 5664 -> 3208 instructions --
 // made it slower, 23.7 -> 24.95 us per force call, so instruction fetch is not what the first pass pays for.)
-template<bool FORCE, bool BUSSI> __device__ __forceinline__ void warp_tree(Acc& a)
+struct Slot
     {
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1)
-        {
-        if (FORCE)
-            {
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                {
-                const double h2 = shfl_xor_d(a.dhi[k], m);
-                const double l2 = shfl_xor_d(a.dlo[k], m);
-                pair_add(a.dhi[k], a.dlo[k], h2, l2);
-                }
-            a.n_L += __shfl_xor_sync(0xffffffffu, a.n_L, m);
-            }
-        if (BUSSI)
-            a.ke += shfl_xor_d(a.ke, m);
-        }
+    double hi, lo; // lanes 8s..8s+7: total of pair s (0..2: dipole x, y, z; 3: KE in hi).  !FORCE: KE in hi, every lane
+    };
+
+__device__ __forceinline__ void slot_butterfly(Slot& v, int m)
+    {
+    const double h2 = shfl_xor_d(v.hi, m), l2 = shfl_xor_d(v.lo, m);
+    pair_add(v.hi, v.lo, h2, l2);
     }
 
-// Second tree level: lane w of warp 0 picks up warp w's totals from shared memory.
-template<bool FORCE, bool BUSSI>
-__device__ __forceinline__ void cross_warp_put(const Acc& a, BlockScratch& sc, unsigned int lane, unsigned int warp)
+// warp total; a.n_L is summed in place (every lane)
+template<bool FORCE, bool BUSSI> __device__ __forceinline__ Slot warp_tree(Acc& a, unsigned int lane)
     {
-    if (lane == 0)
+    Slot v;
+    if (FORCE)
         {
-        if (FORCE)
-            {
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                {
-                sc.red[k][warp] = a.dhi[k];
-                sc.red[3 + k][warp] = a.dlo[k];
-                }
-            sc.red[7][warp] = __longlong_as_double((long long)a.n_L);
-            }
-        if (BUSSI)
-            sc.red[6][warp] = a.ke;
+        const bool up = (lane & 16u) != 0; // upper half keeps (z, KE) and sends (x, y)
+        const double ke = BUSSI ? a.ke : 0.0;
+        double k0h = up ? a.dhi[2] : a.dhi[0], k0l = up ? a.dlo[2] : a.dlo[0];
+        double k1h = up ? ke : a.dhi[1], k1l = up ? 0.0 : a.dlo[1];
+        const double s0h = up ? a.dhi[0] : a.dhi[2], s0l = up ? a.dlo[0] : a.dlo[2];
+        const double s1h = up ? a.dhi[1] : ke, s1l = up ? a.dlo[1] : 0.0;
+        const double r0h = shfl_xor_d(s0h, 16), r0l = shfl_xor_d(s0l, 16);
+        const double r1h = shfl_xor_d(s1h, 16), r1l = shfl_xor_d(s1l, 16);
+        pair_add(k0h, k0l, r0h, r0l);
+        pair_add(k1h, k1l, r1h, r1l);
+        const bool up8 = (lane & 8u) != 0; // of its two pairs a lane keeps the first (bit 3 clear) or the second
+        v.hi = up8 ? k1h : k0h;
+        v.lo = up8 ? k1l : k0l;
+        const double sh = up8 ? k0h : k1h, sl = up8 ? k0l : k1l;
+        const double rh = shfl_xor_d(sh, 8), rl = shfl_xor_d(sl, 8);
+        pair_add(v.hi, v.lo, rh, rl);
+        slot_butterfly(v, 4);
+        slot_butterfly(v, 2);
+        slot_butterfly(v, 1);
+        a.n_L = __reduce_add_sync(0xffffffffu, a.n_L);
         }
+    else
+        {
+        v.hi = a.ke;
+        v.lo = 0.0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1)
+            v.hi += shfl_xor_d(v.hi, m);
+        }
+    return v;
     }
+
+// Second tree level: the warps' totals go through shared memory, pair s in row s (hi) and 4 + s (lo; row 7 unused),
+// columns skewed by 8 per row so that the read below is conflict-free.
+__device__ __forceinline__ unsigned int red_col(unsigned int slot, unsigned int warp) { return (warp + 8u * slot) & 31u; }
+
 template<bool FORCE, bool BUSSI>
-__device__ __forceinline__ void cross_warp_get(Acc& b, const BlockScratch& sc, unsigned int lane, unsigned int nwarps)
+__device__ __forceinline__ void cross_warp_put(const Slot& v, unsigned int n_L, BlockScratch& sc, unsigned int lane,
+                                               unsigned int warp)
     {
-    acc_zero(b);
-    if (lane < nwarps)
+    if (FORCE)
         {
-        if (FORCE)
+        if ((lane & 7u) == 0)
             {
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                {
-                b.dhi[k] = sc.red[k][lane];
-                b.dlo[k] = sc.red[3 + k][lane];
-                }
-            b.n_L = (unsigned int)__double_as_longlong(sc.red[7][lane]);
+            const unsigned int slot = lane >> 3;
+            sc.red[slot][red_col(slot, warp)] = v.hi;
+            if (slot < 3)
+                sc.red[4 + slot][red_col(slot, warp)] = v.lo;
             }
-        if (BUSSI)
-            b.ke = sc.red[6][lane];
+        if (lane == 0)
+            sc.red_nl[warp] = n_L;
         }
-    warp_tree<FORCE, BUSSI>(b);
+    else if (lane == 0)
+        sc.red[3][red_col(3, warp)] = v.hi;
+    }
+// warp 0 only.  Lane 8s + j sums pair s of warps j, j + 8, j + 16, j + 24 -- paired (j, j+16), (j+8, j+24), then those two,
+// the butterfly's order again -- and three exchanges finish it.  Returns the CTA totals as a Slot; n_L in every lane.
+template<bool FORCE, bool BUSSI>
+__device__ __forceinline__ Slot cross_warp_get(unsigned int& n_L, const BlockScratch& sc, unsigned int lane,
+                                               unsigned int nwarps)
+    {
+    Slot v;
+    n_L = 0;
+    if (FORCE)
+        {
+        const unsigned int slot = lane >> 3, j = lane & 7u;
+        Slot w[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            {
+            const unsigned int wi = j + 8u * c;
+            const bool have = wi < nwarps;
+            w[c].hi = have ? sc.red[slot][red_col(slot, wi)] : 0.0;
+            w[c].lo = (have && slot < 3) ? sc.red[4 + slot][red_col(slot, wi)] : 0.0;
+            }
+        if (nwarps > 16)
+            {
+            pair_add(w[0].hi, w[0].lo, w[2].hi, w[2].lo);
+            pair_add(w[1].hi, w[1].lo, w[3].hi, w[3].lo);
+            }
+        if (nwarps > 8)
+            pair_add(w[0].hi, w[0].lo, w[1].hi, w[1].lo);
+        v = w[0];
+        slot_butterfly(v, 4);
+        slot_butterfly(v, 2);
+        slot_butterfly(v, 1);
+        n_L = __reduce_add_sync(0xffffffffu, lane < nwarps ? sc.red_nl[lane] : 0u);
+        }
+    else
+        {
+        v.hi = lane < nwarps ? sc.red[3][red_col(3, lane)] : 0.0;
+        v.lo = 0.0;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1)
+            v.hi += shfl_xor_d(v.hi, m);
+        }
+    return v;
+    }
+// the lanes that hold a total write it into the merged record (lane 0 of each group of eight; KE: lane 24, or lane 0 of
+// a Bussi-only fold); a __syncwarp() must follow before another lane reads sc.rec
+template<bool FORCE, bool BUSSI> __device__ __forceinline__ void slot_to_record(const Slot& v, Partial& rec, unsigned int lane)
+    {
+    if (FORCE)
+        {
+        if ((lane & 7u) == 0)
+            {
+            const unsigned int slot = lane >> 3;
+            if (slot < 3)
+                {
+                rec.dhi[slot] = v.hi;
+                rec.dlo[slot] = v.lo;
+                }
+            else
+                rec.ke = BUSSI ? v.hi : 0.0;
+            }
+        }
+    else if (lane == 0)
+        {
+        for (int k = 0; k < 3; k++)
+            rec.dhi[k] = rec.dlo[k] = 0.0;
+        rec.ke = v.hi;
+        }
     }
 
 __device__ __forceinline__ void unwrap_term(const double4& p, double c, int ix, int iy, int iz, const ForceIn& f,
@@ -393,23 +480,18 @@ __device__ __forceinline__ void block_merge(Acc& a, const ForceIn& f, BlockScrat
                 }
             }
         }
-    warp_tree<FORCE, BUSSI>(a);
-    cross_warp_put<FORCE, BUSSI>(a, sc, lane, warp);
+    const Slot v = warp_tree<FORCE, BUSSI>(a, lane);
+    cross_warp_put<FORCE, BUSSI>(v, a.n_L, sc, lane, warp);
     __syncthreads();
     if (warp == 0)
         {
-        Acc b;
-        cross_warp_get<FORCE, BUSSI>(b, sc, lane, nwarps);
+        unsigned int n_L;
+        const Slot b = cross_warp_get<FORCE, BUSSI>(n_L, sc, lane, nwarps);
+        slot_to_record<FORCE, BUSSI>(b, sc.rec, lane);
         if (lane == 0)
             {
-            for (int k = 0; k < 3; k++)
-                {
-                sc.rec.dhi[k] = b.dhi[k];
-                sc.rec.dlo[k] = b.dlo[k];
-                }
-            sc.rec.ke = b.ke;
-            sc.rec.n_L = b.n_L;
-            if (b.n_L > 1 && sc.rec.first_L != ~0ull)
+            sc.rec.n_L = n_L;
+            if (n_L > 1 && sc.rec.first_L != ~0ull)
                 sc.rec.first_L |= MULTI_L_BIT;
             }
         }
@@ -574,6 +656,7 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
     if (warp < work_warps)
         {
         Acc a;
+        Slot v;
         acc_zero(a);
         unsigned long long mykey = ~0ull;
         unsigned int mycnt = 0, mymulti = 0;
@@ -694,7 +777,7 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
                 if (!FINALIZE) // a rank-level merge may lose the global vote later: keep the term too
                     s4 = read_sector<WAIT, SYS>(reinterpret_cast<const double4*>(recs + myrec) + 4, epoch, late);
                 }
-            warp_tree<FORCE, BUSSI>(a);
+            v = warp_tree<FORCE, BUSSI>(a, lane);
             if (i_hold)
                 {
                 sc.wq[warp][0] = s3.x;
@@ -711,8 +794,8 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
                 }
             }
         else
-            warp_tree<FORCE, BUSSI>(a);
-        cross_warp_put<FORCE, BUSSI>(a, sc, lane, warp);
+            v = warp_tree<FORCE, BUSSI>(a, lane);
+        cross_warp_put<FORCE, BUSSI>(v, 0u, sc, lane, warp);
         if (late)
             atomicOr(&sc.flags, 1u);
         }
@@ -721,8 +804,8 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
         dbg[5] = globaltimer_ns();
     if (warp == 0)
         {
-        Acc t;
-        cross_warp_get<FORCE, BUSSI>(t, sc, lane, work_warps);
+        unsigned int unused_n_L;
+        Slot t = cross_warp_get<FORCE, BUSSI>(unused_n_L, sc, lane, work_warps);
         unsigned long long gmin = ~0ull;
         int many = 0;
         if (FORCE)
@@ -765,10 +848,8 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
                         two_sum_acc(extra.dhi[2], extra.dlo[2], s4.z);
                         }
                     }
-                warp_tree<true, false>(extra);
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    pair_add(t.dhi[k], t.dlo[k], extra.dhi[k], extra.dlo[k]);
+                const Slot e = warp_tree<true, false>(extra, lane); // pair 3 of it is zero
+                pair_add(t.hi, t.lo, e.hi, e.lo);
                 if (late2)
                     atomicOr(&sc.flags, 1u);
                 }
@@ -782,14 +863,10 @@ __device__ __forceinline__ void combine_phase(const Partial* __restrict__ recs, 
                 sc.rec.t[2] = t2;
                 }
             }
+        slot_to_record<FORCE, BUSSI>(t, sc.rec, lane);
+        __syncwarp();
         if (lane == 0)
             {
-            for (int k = 0; k < 3; k++)
-                {
-                sc.rec.dhi[k] = t.dhi[k];
-                sc.rec.dlo[k] = t.dlo[k];
-                }
-            sc.rec.ke = t.ke;
             sc.rec.n_L = many ? 2ull : (gmin != ~0ull ? 1ull : 0ull);
             sc.rec.first_L = gmin == ~0ull ? gmin : (gmin | (many ? MULTI_L_BIT : 0ull));
             if (dbg)
