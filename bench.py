@@ -760,6 +760,14 @@ def run_b200(args):
         b.record(st)
     capi.sync()
     t_step = float(np.mean([b.elapsed_ms_since(a) for a, b in evs]))
+    # what the same two events measure around a kernel that does nothing (one CTA, returns at once): the part of every
+    # "isolated" figure that is the launch and the two event records, not the kernel
+    for k, (a, b) in enumerate(evs):
+        a.record(st)
+        h.debug_delay(0, st)
+        b.record(st)
+    capi.sync()
+    t_empty = float(np.mean([b.elapsed_ms_since(a) for a, b in evs]))
     evs = [(capi.Event(), capi.Event(), capi.Event()) for _ in range(min(K, 200))]
     for k, (a, b, c) in enumerate(evs):
         d = systems[k % len(systems)]
@@ -979,7 +987,9 @@ def run_b200(args):
                                          "the start-to-start period is the throughput figure)"},
             "isolated": {"kernel_ms": t_step, "achieved": STEP_BYTES * N / (t_step * 1e-3) / 1e9,
                          "frac": STEP_BYTES * N / (t_step * 1e-3) / 1e9 / peak,
-                         "note": "CUDA events around every single launch (no launch overlap)"},
+                         "empty_kernel_ms": t_empty,
+                         "note": "CUDA events around every single launch (no launch overlap); empty_kernel_ms is the same "
+                                 "pair of events around a kernel that returns at once"},
         },
         "separate_calls": {
             "value": world * N * K / (ms_sep * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_sep / K,

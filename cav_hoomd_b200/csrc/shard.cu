@@ -138,6 +138,9 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     __shared__ BlockScratch sc;
     const unsigned long long epoch = seq | SHARD_EPOCH_TAG;
     const size_t slot = (size_t)(seq & 1ull) * 16;
+    // programmatic dependent launch (as the single-GPU kernels, hotpath.cu): nothing below may touch global memory before
+    // the previous kernel of the stream has completed
+    pdl_wait();
     if (threadIdx.x == 0)
         sc.flags = 0u;
     reduce_phase<true, false, UNROLL>(f, b, sc);
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     combine_phase<false, true, true, true, true>(my_mailbox + 32 + slot, nranks, epoch, f, b, sc, scalars, blockIdx.x == 0);
     if (sc.fin.timeout || timeout_f)
         return;
+    pdl_launch_dependents(); // the next kernel's CTAs may take the SMs this grid's CTAs leave
     apply_phase<false, true, UNROLL>(sc.fin, f, b);
     }
 
@@ -265,9 +269,24 @@ template<int UNROLL, int LB> static int launch_shard_t(cavb200_handle* h, const 
             g = per_sm * h->num_sms;
         if (g > MAX_PARTIALS / 2)
             g = MAX_PARTIALS / 2;
-        k_shard_split<UNROLL, LB><<<g, threads, 0, s>>>(f, b, h->partials, h->partials + MAX_PARTIALS / 2, h->scalars,
-                                                        sh.gather, sh.rank, nranks, sh.seq, peers);
-        CAVB_CHECK(cudaGetLastError());
+        ForceIn ff = f;
+        BussiIn bb = b;
+        Partial *recsF = h->partials, *recsB = h->partials + MAX_PARTIALS / 2;
+        Scalars* sca = h->scalars;
+        const Partial* box = sh.gather;
+        int rank = sh.rank, nr = nranks;
+        unsigned long long seq = sh.seq;
+        void* args[] = {&ff, &bb, &recsF, &recsB, &sca, &box, &rank, &nr, &seq, &peers};
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(g);
+        cfg.blockDim = dim3(threads);
+        cfg.stream = s;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = h->tune.pdl ? 1 : 0;
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_shard_split<UNROLL, LB>, args));
         h->launches += 1;
         return 0;
         }

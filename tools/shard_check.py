@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--modes", default="nvlink,nccl")
     ap.add_argument("--variant", type=int, default=3, help="tuning variant of the handle")
+    ap.add_argument("--set", default="", help="extra tuning keys for the timed handle, e.g. pdl=0")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -72,6 +73,8 @@ def main():
     for mode in args.modes.split(","):
         h = capi.Handle(local)
         h.set_tuning(variant=args.variant)
+        if args.set:
+            h.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in args.set.split(","))})
         shard.bootstrap(h, dist, mode)
         # ---- parity on a size the CPU oracle finishes in a second ----
         s = synth.make_system(args.check_n)
