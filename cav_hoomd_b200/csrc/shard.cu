@@ -170,7 +170,11 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     __syncthreads();
     combine_phase<false, true, true, true, true>(my_mailbox + 32 + slot, nranks, epoch, f, b, sc, scalars, blockIdx.x == 0);
     if (sc.fin.timeout || timeout_f)
+        {
+        if (threadIdx.x == 0)
+            raise_fault(scalars); // a record never arrived: outputs not (all) written, counted in cavb200_fault_count
         return;
+        }
     pdl_launch_dependents(); // the next kernel's CTAs may take the SMs this grid's CTAs leave
     apply_phase<false, true, UNROLL>(sc.fin, f, b);
     }
@@ -281,11 +285,21 @@ template<int UNROLL, int LB> static int launch_shard_t(cavb200_handle* h, const 
         cfg.gridDim = dim3(g);
         cfg.blockDim = dim3(threads);
         cfg.stream = s;
+        // as hotpath.cu: programmatic dependent launch, or -- tuning pdl=0 -- the cooperative attribute, with which the
+        // driver itself refuses a grid that cannot be co-resident
         cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr.val.programmaticStreamSerializationAllowed = 1;
+        if (h->tune.pdl)
+            {
+            attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr.val.programmaticStreamSerializationAllowed = 1;
+            }
+        else
+            {
+            attr.id = cudaLaunchAttributeCooperative;
+            attr.val.cooperative = 1;
+            }
         cfg.attrs = &attr;
-        cfg.numAttrs = h->tune.pdl ? 1 : 0;
+        cfg.numAttrs = 1;
         CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_shard_split<UNROLL, LB>, args));
         h->launches += 1;
         return 0;

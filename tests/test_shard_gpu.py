@@ -53,3 +53,29 @@ def test_shard_index_offset(coracle):
     assert np.abs(d_f.numpy() - ref["force"]).max() <= 1e-10 * np.abs(ref["force"]).max()
     assert np.array_equal(dev["vel"].numpy(), s.vel)
     h.close()
+
+
+def test_shard_step_launch_modes_bitwise():
+    """The one-kernel sharded step under programmatic dependent launch (default) and under the cooperative attribute
+    (tuning pdl=0, what a handle falls back to after a missed hand-off): same bits, several steps back to back on one
+    stream so that consecutive launches really overlap their tails."""
+    n_mol = 100_003
+    s = synth.make_system(n_mol)
+    p = capi.Params.make(0.01, 1e-3)
+    dof = 3.0 * n_mol - 3
+    a = capi.BussiArgs(synth.KT_100K, synth.TAU_5PS, synth.DT_1FS, dof, 0.3, (dof - 1) / 2)
+    out = {}
+    for pdl in (1, 0):
+        h = capi.Handle(0)
+        h.set_tuning(pdl=pdl)
+        dev = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+        d_f = capi.DeviceArray.from_numpy(np.full((s.N, 4), np.nan))
+        h.bussi_reset()
+        for _ in range(5):  # velocities are rescaled five times over: every launch reads what the previous one wrote
+            h.shard_step(dev["pos"], dev["charge"], dev["image"], d_f, dev["vel"], s.N, 0, s.box, s.L_typeid, p, 0, n_mol, a)
+        out[pdl] = (d_f.numpy(), dev["vel"].numpy(), h.force_read()[0], h.bussi_read())
+        assert h.fault_count == 0
+        h.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2]) and out[0][3] == out[1][3]
+    assert not np.array_equal(out[1][1], s.vel)
