@@ -172,6 +172,8 @@ int cavb200_create(cavb200_handle** out, int device)
     h->tune.pdl = 1;
     h->tune.auto_threads = 1;
     h->tune.small_n = 1024;
+    h->tune.cluster_n = 8192;
+    h->tune.cluster_ctas = 16;
     h->shard.mode = 0;
     h->shard.nranks = 1;
     *out = h;
@@ -220,6 +222,8 @@ static int* tuning_slot(cavb::Tuning* t, const char* key)
     if (!strcmp(key, "auto_threads")) return &t->auto_threads;
     if (!strcmp(key, "md_shape")) return &t->md_shape;
     if (!strcmp(key, "small_n")) return &t->small_n;
+    if (!strcmp(key, "cluster_n")) return &t->cluster_n;
+    if (!strcmp(key, "cluster_ctas")) return &t->cluster_ctas;
     return nullptr;
     }
 

@@ -94,6 +94,9 @@ struct Tuning
     int auto_threads;    // step kernel: pick 320 / 352 / 384 threads per CTA from the particle count (1) or use `threads` (0)
     int ke_first;        // folder step kernel: thermostat half first (1) or dipole half first (0)
     int small_n;         // calls over at most this many particles run as ONE CTA with no inter-CTA hand-off (0: off)
+    int cluster_n;       // ... and, for calls that include the force, up to this many as ONE thread-block cluster of 16 CTAs:
+                         //     hardware barrier instead of polled records (0: off; with a cluster of 8, half as many)
+    int cluster_ctas;    // CTAs of that cluster (16 = non-portable size; the launcher falls back to 8 if the device refuses it)
     };
 
 struct ShardState
@@ -255,6 +258,24 @@ __device__ __forceinline__ double ld_charge_last(const double* p)
 
 // programmatic dependent launch: wait for the previous kernel of the stream / let the next one start
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// thread-block cluster: rank and size of this CTA's cluster, and the hardware barrier over all its threads (release /
+// acquire at cluster scope: what a thread wrote before it, to global memory too, is visible to every thread after it)
+__device__ __forceinline__ unsigned int cluster_ctarank()
+    {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+    }
+__device__ __forceinline__ unsigned int cluster_nctarank()
+    {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+    }
+__device__ __forceinline__ void cluster_sync()
+    {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)

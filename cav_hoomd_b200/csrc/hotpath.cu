@@ -441,6 +441,39 @@ __global__ void __launch_bounds__(1024, 1) k_small(ForceIn f, BussiIn b, Scalars
     apply_phase<FORCE, BUSSI, 2, LIST>(sc.fin, f, b, g);
     }
 
+// Systems between small_n and cluster_n particles: ONE thread-block cluster does the whole call.  The CTAs of a cluster
+// are co-scheduled by the hardware and share a hardware barrier, so the hand-off needs neither polling nor epochs nor a
+// time-out: every CTA stores its record (L2), barrier.cluster (release / acquire), every CTA folds the <= 16 records for
+// itself -- the same fold, in the same order, as the persistent kernels' -- and applies.  Measured against the persistent
+// kernels (profiles/cluster_n_r2a.txt, cluster of 16): the one-launch step 6.4 against 8.3 us at 1.5k-4k particles, 7.3
+// against 8.6 us at 8k, slower from 16k on; the force call 4.9 against 5.4 us (equal at 8k); the Bussi call no better at
+// any size -- so: calls with the force in them, up to tuning cluster_n (8192) particles.
+template<bool FORCE, bool BUSSI, bool LIST>
+__global__ void __launch_bounds__(1024, 1) k_cluster(ForceIn f, BussiIn b, Partial* recs, Scalars* scalars, Final* fin_out)
+    {
+    __shared__ BlockScratch sc;
+    pdl_wait();
+    if (threadIdx.x == 0)
+        sc.flags = 0u;
+    StreamGrid g;
+    g.nblk = cluster_nctarank();
+    g.blk = cluster_ctarank();
+    reduce_phase<FORCE, BUSSI, 2, LIST>(f, b, sc, g);
+    if (threadIdx.x == 0)
+        publish_record(recs + g.blk, sc.rec, 0ull);
+    cluster_sync();
+    combine_phase<FORCE, BUSSI, false, true>(recs, (int)g.nblk, 0ull, f, b, sc, scalars, g.blk == 0, nullptr);
+    if (FORCE && !BUSSI && f.force == nullptr)
+        {
+        if (g.blk == 0 && threadIdx.x == 0)
+            *fin_out = sc.fin; // rank-1 mode: the consumers read Dq / F_L from here
+        pdl_launch_dependents();
+        return;
+        }
+    pdl_launch_dependents();
+    apply_phase<FORCE, BUSSI, 2, LIST>(sc.fin, f, b, g);
+    }
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -482,6 +515,62 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
             CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_small<FORCE, BUSSI, LIST>, args));
             h->launches += 1;
             return 0;
+            }
+        // (the Bussi-only call gains nothing from it: 3.9 us against 3.75 us, profiles/cluster_n_r2a.txt)
+        if (FORCE && h->tune.cluster_n > 0 && h->tune.cluster_ctas >= 2)
+            {
+            // one cluster of 16 CTAs (a non-portable size: asked for once per kernel; if the device cannot place it, 8 from then
+            // on, which pays off for half as many particles), as many threads per CTA as spread the particles one per thread
+            const void* kern = (const void*)k_cluster<FORCE, BUSSI, LIST>;
+            static bool non_portable_set = false; // (per kernel instantiation: launch_t is a template)
+            for (int attempt = 0; attempt < 2; attempt++)
+                {
+                const int ctas = h->tune.cluster_ctas >= 16 ? 16 : (h->tune.cluster_ctas >= 8 ? 8 : (h->tune.cluster_ctas >= 4 ? 4 : 2));
+                if (work_small > (unsigned long long)h->tune.cluster_n * (unsigned long long)ctas / 16ull)
+                    break;
+                if (ctas == 16 && !non_portable_set)
+                    {
+                    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+                        {
+                        cudaGetLastError();
+                        h->tune.cluster_ctas = 8;
+                        continue;
+                        }
+                    non_portable_set = true;
+                    }
+                int t = (int)((work_small + ctas - 1) / ctas);
+                t = (t + 31) / 32 * 32;
+                t = t < 64 ? 64 : (t > 1024 ? 1024 : t);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(ctas);
+                cfg.blockDim = dim3(t);
+                cfg.stream = s;
+                cudaLaunchAttribute attrs[2];
+                attrs[0].id = cudaLaunchAttributeClusterDimension;
+                attrs[0].val.clusterDim.x = ctas;
+                attrs[0].val.clusterDim.y = 1;
+                attrs[0].val.clusterDim.z = 1;
+                attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attrs[1].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attrs;
+                cfg.numAttrs = h->tune.pdl ? 2 : 1;
+                ForceIn ff = f;
+                BussiIn bb = b;
+                Partial* recs = h->partials;
+                Scalars* sca = h->scalars;
+                Final* fo = const_cast<Final*>(rank1_final(h));
+                void* args[] = {&ff, &bb, &recs, &sca, &fo};
+                const cudaError_t e = cudaLaunchKernelExC(&cfg, kern, args);
+                if (e == cudaSuccess)
+                    {
+                    h->launches += 1;
+                    return 0;
+                    }
+                cudaGetLastError();
+                if (ctas != 16)
+                    return (int)e;
+                h->tune.cluster_ctas = 8; // this device (or this share of it) has no room for 16 co-scheduled CTAs
+                }
             }
         }
     int threads = h->tune.threads;

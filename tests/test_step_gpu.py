@@ -342,3 +342,44 @@ def test_single_cta_kernel_for_small_systems(coracle, n_mol, photon):
             assert np.allclose(d_v.numpy(), vref, rtol=1e-12, atol=0)
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("photon", ["last", "first", "middle", "absent", "duplicated"])
+@pytest.mark.parametrize("n_mol,ctas", [(1025, 16), (1537, 8), (3000, 16), (4096, 8), (8191, 16)])
+def test_single_cluster_kernel_for_mid_size_systems(coracle, n_mol, ctas, photon):
+    """Calls that include the force, over more than `small_n` and at most `cluster_n` particles (default 8192), run as ONE
+    thread-block cluster (k_cluster): the CTAs' records meet behind the hardware cluster barrier instead of being polled.
+    Same fold as the persistent kernels, so the same results as with tuning cluster_n = 0 (1e-14; bitwise wherever the
+    partition into CTAs happens to coincide), both checked against the oracle; the one-launch step equals the force call
+    followed by the Bussi call bit for bit in the force, and the rank-1 call leaves the same scalars."""
+    h = capi.Handle(0)
+    try:
+        s = synth.make_system(n_mol, replica=n_mol, photon=photon)
+        first, n = (0, n_mol) if photon in ("last", "absent") else (0, s.N)
+        a = args_for(n)
+        outs = {}
+        for cl in (0, 8192):
+            h.set_tuning(cluster_n=cl, cluster_ctas=ctas)
+            outs[cl] = run_step(h, s, first, n, a)
+            check_against_oracle(coracle, s, first, n, a, outs[cl])
+        f0, v0, en0, dip0, ph0, bo0 = outs[0]
+        f1, v1, en1, dip1, ph1, bo1 = outs[8192]
+        assert ph0 == ph1 and np.abs(f1 - f0).max() <= 1e-14 * max(np.abs(f0).max(), 1e-300)
+        assert np.allclose(v1, v0, rtol=1e-14, atol=0) and abs(bo1["alpha"] - bo0["alpha"]) <= 1e-14
+        assert np.allclose(en1, en0, rtol=1e-13, atol=0) and np.allclose(dip1, dip0, rtol=1e-13, atol=1e-300)
+        # the force call alone takes the cluster kernel too; its forces are those of the one-launch step
+        p = capi.Params.make(0.01, 1e-3)
+        dev = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+        d_f = capi.DeviceArray.from_numpy(np.full((s.N, 4), np.nan))
+        launches = h.launch_count
+        h.force(dev["pos"], dev["charge"], dev["image"], d_f, s.N, s.box, s.L_typeid, p)
+        assert h.launch_count == launches + 1
+        assert np.array_equal(d_f.numpy().view(np.uint64), f1.view(np.uint64))
+        assert np.array_equal(h.force_read()[0], en1)
+        # rank-1 mode (no force array): same scalars
+        h.force_rank1(dev["pos"], dev["charge"], dev["image"], s.N, s.box, s.L_typeid, p)
+        en_r, dip_r, ph_r = h.force_read()
+        assert ph_r == ph1 and np.array_equal(en_r, en1) and np.array_equal(dip_r, dip1)
+        assert h.fault_count == 0
+    finally:
+        h.close()
