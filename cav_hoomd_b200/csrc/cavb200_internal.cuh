@@ -272,6 +272,16 @@ __device__ __forceinline__ unsigned int cluster_nctarank()
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
     return r;
     }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// store 8 bytes into the shared memory of CTA `peer` of this cluster, at the address `local` has in this CTA
+__device__ __forceinline__ void st_dsmem_f64(const void* local, unsigned int peer, double v)
+    {
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(local);
+    unsigned int dst;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(a), "r"(peer));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(dst), "d"(v) : "memory");
+    }
 __device__ __forceinline__ void cluster_sync()
     {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");

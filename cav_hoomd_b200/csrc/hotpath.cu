@@ -442,16 +442,22 @@ __global__ void __launch_bounds__(1024, 1) k_small(ForceIn f, BussiIn b, Scalars
     }
 
 // Systems between small_n and cluster_n particles: ONE thread-block cluster does the whole call.  The CTAs of a cluster
-// are co-scheduled by the hardware and share a hardware barrier, so the hand-off needs neither polling nor epochs nor a
-// time-out: every CTA stores its record (L2), barrier.cluster (release / acquire), every CTA folds the <= 16 records for
-// itself -- the same fold, in the same order, as the persistent kernels' -- and applies.  Measured against the persistent
-// kernels (profiles/cluster_n_r2a.txt, cluster of 16): the one-launch step 6.4 against 8.3 us at 1.5k-4k particles, 7.3
-// against 8.6 us at 8k, slower from 16k on; the force call 4.9 against 5.4 us (equal at 8k); the Bussi call no better at
-// any size -- so: calls with the force in them, up to tuning cluster_n (8192) particles.
+// are co-scheduled by the hardware, can store into each other's shared memory and share a hardware barrier, so the hand-off
+// needs neither global memory nor polling nor epochs nor a time-out: every CTA stores its record into every CTA's inbox
+// (distributed shared memory), barrier.cluster (release / acquire), every CTA folds the <= 16 records for itself -- the same
+// fold, in the same order, as the persistent kernels' -- and applies.  Measured against the persistent kernels
+// (profiles/cluster_n_r2a.txt, cluster of 16): the one-launch step 5.75 against 8.1 us at 1.5k-4k particles, 6.55 against
+// 8.4 us at 8k, equal at 16k; the force call 4.1 against 5.35 us (4.7 against 5.5 at 8k, slower at 16k); force + Bussi 7.8
+// against 9.0 us.  (With the records going through L2 instead of shared memory, as first built: step 6.4, force 4.9 us.)
+// The Bussi-only call is no better at any size -- so: calls with the force in them, up to tuning cluster_n (8192) particles.
 template<bool FORCE, bool BUSSI, bool LIST>
-__global__ void __launch_bounds__(1024, 1) k_cluster(ForceIn f, BussiIn b, Partial* recs, Scalars* scalars, Final* fin_out)
+__global__ void __launch_bounds__(1024, 1) k_cluster(ForceIn f, BussiIn b, Scalars* scalars, Final* fin_out)
     {
     __shared__ BlockScratch sc;
+    __shared__ Partial inbox[16];
+    // (a CTA's shared memory may be written by its peers only once it runs: first half of a barrier now, second half
+    // before the first remote store)
+    cluster_arrive();
     pdl_wait();
     if (threadIdx.x == 0)
         sc.flags = 0u;
@@ -459,10 +465,10 @@ __global__ void __launch_bounds__(1024, 1) k_cluster(ForceIn f, BussiIn b, Parti
     g.nblk = cluster_nctarank();
     g.blk = cluster_ctarank();
     reduce_phase<FORCE, BUSSI, 2, LIST>(f, b, sc, g);
-    if (threadIdx.x == 0)
-        publish_record(recs + g.blk, sc.rec, 0ull);
+    cluster_wait();
+    cluster_post(inbox, sc.rec, g.blk, g.nblk);
     cluster_sync();
-    combine_phase<FORCE, BUSSI, false, true>(recs, (int)g.nblk, 0ull, f, b, sc, scalars, g.blk == 0, nullptr);
+    combine_cluster<FORCE, BUSSI>(inbox, g.nblk, f, b, sc, scalars, g.blk == 0);
     if (FORCE && !BUSSI && f.force == nullptr)
         {
         if (g.blk == 0 && threadIdx.x == 0)
@@ -516,7 +522,7 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
             h->launches += 1;
             return 0;
             }
-        // (the Bussi-only call gains nothing from it: 3.9 us against 3.75 us, profiles/cluster_n_r2a.txt)
+        // (the Bussi-only call gains nothing from it: 3.7-3.9 us either way up to 4k particles, slower above; profiles/cluster_n_r2a.txt)
         if (FORCE && h->tune.cluster_n > 0 && h->tune.cluster_ctas >= 2)
             {
             // one cluster of 16 CTAs (a non-portable size: asked for once per kernel; if the device cannot place it, 8 from then
@@ -556,10 +562,9 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
                 cfg.numAttrs = h->tune.pdl ? 2 : 1;
                 ForceIn ff = f;
                 BussiIn bb = b;
-                Partial* recs = h->partials;
                 Scalars* sca = h->scalars;
                 Final* fo = const_cast<Final*>(rank1_final(h));
-                void* args[] = {&ff, &bb, &recs, &sca, &fo};
+                void* args[] = {&ff, &bb, &sca, &fo};
                 const cudaError_t e = cudaLaunchKernelExC(&cfg, kern, args);
                 if (e == cudaSuccess)
                     {

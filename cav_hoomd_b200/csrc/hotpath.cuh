@@ -971,6 +971,96 @@ __device__ __forceinline__ void finalize(const ForceIn& f, const BussiIn& b, Blo
         }
     }
 
+// ---- hand-off inside ONE thread-block cluster (k_cluster): the records travel through distributed shared memory ---------
+// Every CTA stores its record into the inbox of every CTA of the cluster (st.shared::cluster, 20 words per peer), the cluster
+// barrier orders the stores, and warp 0 of every CTA folds its own inbox: the fold of combine_phase for G <= 32 records -- one
+// record per lane, the same transposed tree, the same vote for the first 'L' particle, the same put-back of the other
+// candidates' terms -- without a global-memory round trip.
+__device__ __forceinline__ void cluster_post(Partial* inbox, const Partial& rec, unsigned int rank, unsigned int nctas)
+    {
+    const double* src = reinterpret_cast<const double*>(&rec);
+    double* slot = reinterpret_cast<double*>(inbox + rank);
+    constexpr unsigned int W = sizeof(Partial) / 8;
+    for (unsigned int w = threadIdx.x; w < W * nctas; w += blockDim.x)
+        st_dsmem_f64(slot + w % W, w / W, src[w % W]);
+    }
+template<bool FORCE, bool BUSSI>
+__device__ __forceinline__ void combine_cluster(const Partial* inbox, unsigned int C, const ForceIn& f, const BussiIn& b,
+                                                BlockScratch& sc, Scalars* scalars, bool publish)
+    {
+    const unsigned int lane = threadIdx.x & 31u;
+    if (threadIdx.x < 32u)
+        {
+        const bool have = lane < C;
+        const Partial& r = inbox[have ? lane : 0u];
+        Acc a;
+        acc_zero(a);
+        unsigned long long key = ~0ull;
+        if (have)
+            {
+            if (FORCE)
+                {
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    pair_add(a.dhi[k], a.dlo[k], r.dhi[k], r.dlo[k]);
+                key = r.first_L;
+                }
+            if (BUSSI)
+                a.ke += r.ke;
+            }
+        Slot t = warp_tree<FORCE, BUSSI>(a, lane);
+        unsigned long long gmin = ~0ull;
+        int many = 0;
+        if (FORCE)
+            {
+            const bool cand = key != ~0ull;
+            const unsigned long long idx = cand ? (key & ~MULTI_L_BIT) : ~0ull;
+            gmin = warp_min_u64(idx);
+            const unsigned int cnt = __popc(__ballot_sync(0xffffffffu, cand));
+            many = (cnt > 1) || __any_sync(0xffffffffu, cand && (key & MULTI_L_BIT) != 0);
+            const unsigned int holders = __ballot_sync(0xffffffffu, cand && idx == gmin);
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+            if (holders)
+                {
+                const int w = __ffs(holders) - 1;
+                q0 = __shfl_sync(0xffffffffu, r.q[0], w);
+                q1 = __shfl_sync(0xffffffffu, r.q[1], w);
+                q2 = __shfl_sync(0xffffffffu, r.q[2], w);
+                }
+            if (many)
+                {
+                // every candidate that is not the global first is an ordinary member of the dipole sum (as combine_phase)
+                Acc extra;
+                acc_zero(extra);
+                if (cand && idx != gmin)
+                    {
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                        two_sum_acc(extra.dhi[k], extra.dlo[k], r.t[k]);
+                    }
+                const Slot e = warp_tree<true, false>(extra, lane);
+                pair_add(t.hi, t.lo, e.hi, e.lo);
+                }
+            if (lane == 0)
+                {
+                sc.rec.q[0] = q0;
+                sc.rec.q[1] = q1;
+                sc.rec.q[2] = q2;
+                sc.rec.t[0] = sc.rec.t[1] = sc.rec.t[2] = 0.0;
+                }
+            }
+        slot_to_record<FORCE, BUSSI>(t, sc.rec, lane);
+        __syncwarp();
+        if (lane == 0)
+            {
+            sc.rec.n_L = many ? 2ull : (gmin != ~0ull ? 1ull : 0ull);
+            sc.rec.first_L = gmin == ~0ull ? gmin : (gmin | (many ? MULTI_L_BIT : 0ull));
+            finalize<FORCE, BUSSI>(f, b, sc, scalars, publish);
+            }
+        }
+    __syncthreads();
+    }
+
 // ------------------------------------------------------------------------------------------
 // apply
 // ------------------------------------------------------------------------------------------
