@@ -572,8 +572,9 @@ def leg_small_n(cx, params):
     if cross is None and rows[0]["cpu_one_core_us"] >= rows[0]["gpu_two_calls_us"]:
         cross = f"below {rows[0]['n_particles']}"
     return {"note": "cavity force + Bussi step at the reference authors' own system size (configs[0]: 500 particles + photon) "
-                    "and up: calls over at most 1024 particles run as ONE CTA (k_small, no inter-CTA hand-off) and are bound "
-                    "by launch latency (python/ctypes host loop; the CUDA-graph column replays 100 steps per launch); the CPU "
+                    "and up: calls over at most 768 particles run as ONE CTA (k_small, no inter-CTA hand-off), calls with the force "
+                    "in them up to 8192 particles as ONE thread-block cluster (k_cluster, records through distributed shared "
+                    "memory); both are bound by launch latency (python/ctypes host loop; the CUDA-graph column replays 100 steps per launch); the CPU "
                     "reference runs out of cache",
             "sweep": rows, "gpu_faster_than_one_core_above_n_particles": cross}
 

@@ -171,7 +171,7 @@ int cavb200_create(cavb200_handle** out, int device)
     h->tune.unroll = 2;
     h->tune.pdl = 1;
     h->tune.auto_threads = 1;
-    h->tune.small_n = 1024;
+    h->tune.small_n = 768;
     h->tune.cluster_n = 8192;
     h->tune.cluster_ctas = 16;
     h->shard.mode = 0;

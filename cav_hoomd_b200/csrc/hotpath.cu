@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
     ring_end(stamps, stamp_mode, epoch);
     }
 
-// Small systems (tuning "small_n", default 1024 particles; the reference's own example runs 501): ONE CTA does the whole
+// Small systems (tuning "small_n", default 768 particles; the reference's own example runs 501): ONE CTA does the whole
 // call -- reduce, block merge, finalize, apply -- so there is no hand-off between CTAs at all.  At 501 particles the
 // two-CTA persistent kernels take 5.5 / 3.7 / 8.7 us (force / Bussi / step), nearly all of it the global-memory hand-off;
 // this one takes 3.8 / 3.3 / 6.2 us and is bound by its chain of latencies (profiles/small_n_r2a.txt: it wins below ~1000
@@ -531,9 +531,11 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
             static bool non_portable_set = false; // (per kernel instantiation: launch_t is a template)
             for (int attempt = 0; attempt < 2; attempt++)
                 {
-                const int ctas = h->tune.cluster_ctas >= 16 ? 16 : (h->tune.cluster_ctas >= 8 ? 8 : (h->tune.cluster_ctas >= 4 ? 4 : 2));
-                if (work_small > (unsigned long long)h->tune.cluster_n * (unsigned long long)ctas / 16ull)
+                const int cmax = h->tune.cluster_ctas >= 16 ? 16 : (h->tune.cluster_ctas >= 8 ? 8 : (h->tune.cluster_ctas >= 4 ? 4 : 2));
+                if (work_small > (unsigned long long)h->tune.cluster_n * (unsigned long long)cmax / 16ull)
                     break;
+                // (up to 2k particles 8 CTAs are as fast as 16, and steadier: 1001 particles, step 5.5 against 6.6 us)
+                const int ctas = (cmax == 16 && work_small <= 2048ull) ? 8 : cmax;
                 if (ctas == 16 && !non_portable_set)
                     {
                     if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)

@@ -112,7 +112,7 @@ int cavb200_debug_delay(cavb200_handle* h, uint64_t ns, void* stream);
 int cavb200_debug_fp64_peak(cavb200_handle* h, double* dfma_per_s);
 int cavb200_debug_launch_ring(cavb200_handle* h, int reset, uint64_t* out, uint32_t n_pairs, uint64_t* epoch);
 /* Tuning knobs ("variant", "threads", "ctas_per_sm", "unroll", "pdl", "stamps", ...); unknown key -> 1.
- * By size: calls over at most "small_n" particles (1024) run as one CTA; calls that include the force, over at most
+ * By size: calls over at most "small_n" particles (768) run as one CTA; calls that include the force, over at most
  * "cluster_n" particles (8192), as one thread-block cluster of "cluster_ctas" CTAs (16; 8 and half the size if the device
  * refuses the non-portable cluster size); everything else as persistent grids.  0 switches either off. */
 int cavb200_set_tuning(cavb200_handle* h, const char* key, int value);

@@ -298,7 +298,7 @@ def test_step_randomised_cases(coracle):
 @pytest.mark.parametrize("photon", ["last", "first", "middle", "absent", "duplicated"])
 @pytest.mark.parametrize("n_mol", [1, 2, 33, 385, 500, 799])
 def test_single_cta_kernel_for_small_systems(coracle, n_mol, photon):
-    """Calls over at most `small_n` particles (default 1024; the reference's own example has 501) run as ONE CTA without
+    """Calls over at most `small_n` particles (default 768; the reference's own example has 501) run as ONE CTA without
     any inter-CTA hand-off (k_small).  Same results as the multi-CTA persistent kernels (tuning small_n = 0) -- the dipole
     to the last bit or two (another partition of the same compensated sum), everything else 1e-14 -- both against the
     oracle; the one-launch step stays bit-identical to the two calls; index-list and windowed groups included."""
@@ -308,6 +308,7 @@ def test_single_cta_kernel_for_small_systems(coracle, n_mol, photon):
         first, n = (0, n_mol) if photon in ("last", "absent") else (0, s.N)
         a = args_for(n)
         outs = {}
+        h.set_tuning(cluster_n=0)  # (small_n = 0 alone would send these sizes to the single-cluster kernel, tested below)
         for small in (0, 800):
             h.set_tuning(small_n=small)
             outs[small] = run_step(h, s, first, n, a)
