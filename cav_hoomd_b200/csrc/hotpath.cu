@@ -414,8 +414,8 @@ __global__ void __launch_bounds__(LB, LB == 384 ? 2 : 1)
 // Small systems (tuning "small_n", default 768 particles; the reference's own example runs 501): ONE CTA does the whole
 // call -- reduce, block merge, finalize, apply -- so there is no hand-off between CTAs at all.  At 501 particles the
 // two-CTA persistent kernels take 5.5 / 3.7 / 8.7 us (force / Bussi / step), nearly all of it the global-memory hand-off;
-// this one takes 3.8 / 3.3 / 6.2 us and is bound by its chain of latencies (profiles/small_n_r2a.txt: it wins below ~1000
-// particles).  Same per-thread orders and the same merge trees for the step as for the two calls, so cavb200_step stays
+// this one takes 3.5 / 3.4 / 5.3 us and is bound by its chain of latencies (profiles/small_n_r2a.txt: it beats the
+// persistent kernels below ~1000 particles and the single-cluster kernel below ~700).  Same per-thread orders and the same merge trees for the step as for the two calls, so cavb200_step stays
 // bit-identical to cavb200_force + cavb200_bussi.
 template<bool FORCE, bool BUSSI, bool LIST>
 __global__ void __launch_bounds__(1024, 1) k_small(ForceIn f, BussiIn b, Scalars* scalars, Final* fin_out)
