@@ -173,7 +173,7 @@ int cavb200_create(cavb200_handle** out, int device)
     h->tune.auto_threads = 1;
     h->tune.small_n = 768;
     h->tune.cluster_n = 8192;
-    h->tune.cluster_ctas = 16;
+    h->tune.cluster_ctas = cluster_kernels_init();
     h->shard.mode = 0;
     h->shard.nranks = 1;
     *out = h;

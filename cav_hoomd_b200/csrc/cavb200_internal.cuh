@@ -387,6 +387,7 @@ struct Final;
 inline const Final* rank1_final(const cavb200_handle* h) { return reinterpret_cast<const Final*>(h->counters + 32); }
 void fill_bussi_constants(BussiIn& b, const cavb200_bussi_args* a);
 int launch_hotpath(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cudaStream_t s);
+int cluster_kernels_init();
 int launch_shard_step(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cudaStream_t s);
 // top of every compute entry point: a hand-off timeout reported by an earlier launch (Scalars::fault) switches the handle
 // to cooperative launches for good and is returned ONCE as cudaErrorLaunchTimeout

@@ -525,10 +525,10 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         // (the Bussi-only call gains nothing from it: 3.7-3.9 us either way up to 4k particles, slower above; profiles/cluster_n_r2a.txt)
         if (FORCE && h->tune.cluster_n > 0 && h->tune.cluster_ctas >= 2)
             {
-            // one cluster of 16 CTAs (a non-portable size: asked for once per kernel; if the device cannot place it, 8 from then
-            // on, which pays off for half as many particles), as many threads per CTA as spread the particles one per thread
+            // one cluster of 16 CTAs (a non-portable size: allowed per kernel at handle creation, cluster_kernels_init; if the
+            // device cannot place it, 8 from then on, which pays off for half as many particles), as many threads per CTA
+            // as spread the particles one per thread
             const void* kern = (const void*)k_cluster<FORCE, BUSSI, LIST>;
-            static bool non_portable_set = false; // (per kernel instantiation: launch_t is a template)
             for (int attempt = 0; attempt < 2; attempt++)
                 {
                 const int cmax = h->tune.cluster_ctas >= 16 ? 16 : (h->tune.cluster_ctas >= 8 ? 8 : (h->tune.cluster_ctas >= 4 ? 4 : 2));
@@ -536,16 +536,6 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
                     break;
                 // (up to 2k particles 8 CTAs are as fast as 16, and steadier: 1001 particles, step 5.5 against 6.6 us)
                 const int ctas = (cmax == 16 && work_small <= 2048ull) ? 8 : cmax;
-                if (ctas == 16 && !non_portable_set)
-                    {
-                    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
-                        {
-                        cudaGetLastError();
-                        h->tune.cluster_ctas = 8;
-                        continue;
-                        }
-                    non_portable_set = true;
-                    }
                 int t = (int)((work_small + ctas - 1) / ctas);
                 t = (t + 31) / 32 * 32;
                 t = t < 64 ? 64 : (t > 1024 ? 1024 : t);
@@ -817,6 +807,20 @@ static int launch_u(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
             return launch_t<FORCE, BUSSI, 2, 768>(h, f, b, s);
         return launch_t<FORCE, BUSSI, 2, 1024>(h, f, b, s);
         }
+    }
+
+// Called once per handle (cavb200_create), outside any stream capture: allow the cluster kernels the non-portable
+// cluster size of 16.  Returns the largest cluster the launcher may ask for.
+int cluster_kernels_init()
+    {
+    const void* kerns[] = {(const void*)k_cluster<true, false, false>, (const void*)k_cluster<true, true, false>};
+    for (const void* k : kerns)
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+            {
+            cudaGetLastError();
+            return 8;
+            }
+    return 16;
     }
 
 int launch_hotpath(cavb200_handle* h, const ForceIn* f, const BussiIn* b, cudaStream_t s)

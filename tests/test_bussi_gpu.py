@@ -157,6 +157,40 @@ def test_fused_step_equals_separate_calls(handle, coracle, n_mol, variant):
     assert np.allclose(v_fused, vref, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("n_mol", [500, 3000])
+def test_small_system_kernels_under_cuda_graph(coracle, n_mol):
+    """The single-CTA kernel (500 particles) and the single-cluster kernel (3000 particles: cluster launch attribute, 16
+    CTAs) captured in a CUDA graph as the FIRST thing a fresh handle does -- nothing the launcher needs may be set up
+    lazily inside the capture -- and replayed: force call + Bussi call, three steps."""
+    h = capi.Handle(0)
+    try:
+        s = synth.make_system(n_mol)
+        p = capi.Params.make(0.01, 1e-3)
+        a = bargs(3.0 * n_mol - 3.0)
+        dev = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+        d_f = capi.DeviceArray.from_numpy(np.full((s.N, 4), np.nan))
+        st = capi.Stream()
+
+        def two_calls():
+            h.force(dev["pos"], dev["charge"], dev["image"], d_f, s.N, s.box, s.L_typeid, p, st.ptr)
+            h.bussi(dev["vel"], None, 0, n_mol, a, st.ptr)
+
+        g = h.graph_capture(st.ptr, two_calls)
+        vref = s.vel.copy()
+        res = np.zeros(2)
+        for _ in range(3):
+            h.graph_launch(g, st.ptr)
+            coracle.bussi_step(vref, np.arange(n_mol, dtype=np.uint32), a.dof, DT, KT, TAU, a.r_normal, a.gamma_draw, res)
+        st.sync()
+        h.graph_destroy(g)
+        assert np.allclose(dev["vel"].numpy(), vref, rtol=1e-11, atol=0)
+        ref = coracle.cavity_force(s.pos, s.charge, s.image, s.box, s.L_typeid, 0.01, 1e-3)
+        assert np.abs(d_f.numpy() - ref["force"]).max() <= 1e-10 * np.abs(ref["force"]).max()
+        assert h.fault_count == 0
+    finally:
+        h.close()
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3])
 def test_step_under_cuda_graph(handle, coracle, variant):
     """The step captured in a CUDA graph and replayed gives the same result as direct launches
