@@ -384,3 +384,34 @@ def test_single_cluster_kernel_for_mid_size_systems(coracle, n_mol, ctas, photon
         assert h.fault_count == 0
     finally:
         h.close()
+
+
+def test_cluster_kernel_back_to_back_launches_of_different_shapes():
+    """600 force calls back to back on one stream, alternating between three systems whose calls take a cluster of 8
+    (1500 particles), a cluster of 16 (6000) and the single CTA (400): consecutive launches overlap under programmatic
+    dependent launch, each with its own shared-memory inboxes.  Every launch must reproduce the bits of its system's
+    first result."""
+    h = capi.Handle(0)
+    try:
+        p = capi.Params.make(0.01, 1e-3)
+        st = capi.Stream()
+        systems = []
+        for n_mol in (1500, 6000, 400):
+            s = synth.make_system(n_mol, replica=n_mol)
+            d = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image")}
+            outs = [capi.DeviceArray.from_numpy(np.full((s.N, 4), np.nan)) for _ in range(4)]
+            h.force(d["pos"], d["charge"], d["image"], outs[0], s.N, s.box, s.L_typeid, p, st.ptr)
+            first = (outs[0].numpy(st.ptr).copy(), h.force_read(st.ptr)[0].copy())
+            systems.append((s, d, outs, first))
+        for k in range(600):
+            s, d, outs, first = systems[k % 3]
+            h.force(d["pos"], d["charge"], d["image"], outs[1 + (k // 3) % 3], s.N, s.box, s.L_typeid, p, st.ptr)
+        st.sync()
+        for s, d, outs, first in systems:
+            for o in outs[1:]:
+                assert np.array_equal(o.numpy(st.ptr).view(np.uint64), first[0].view(np.uint64))
+        # the scalars left behind are those of the last call (system index 599 % 3 = 2)
+        assert np.array_equal(h.force_read(st.ptr)[0], systems[2][3][1])
+        assert h.fault_count == 0
+    finally:
+        h.close()
