@@ -798,14 +798,52 @@ static int launch_u(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
             return (int)cudaErrorInvalidConfiguration;
         return launch_t<FORCE, BUSSI, 4, 512>(h, f, b, s);
     default:
+        {
         // two 384-thread CTAs per SM (24 warps, 80 registers): the shape that keeps the fused
         // force + KE loop out of local memory (profiles/microprod_r1b.txt); wider CTAs fall back
         // to the 64-register build
+        //
+        // Below ~2M particles ONE CTA per SM is the better shape for some calls -- half as many records to fold, and the
+        // hand-off is a larger share of a short call (profiles/shapes_r2b.txt, us per call, default -> this rule):
+        //   force call   65k 8.1 -> 7.0    131k 10.0 -> 8.3   262k 11.8 -> 10.6   524k 15.2 -> 14.2   1M 20.8 -> 20.3   2M+ equal
+        //   Bussi call   16k 5.3 -> 4.0    65k 5.1 -> 4.1     131k 5.2 -> 4.8     262k 6.3 -> 6.2     400k+ no better or worse
+        //   step         65k 9.6 -> 9.3    131k 13.1 -> 11.3  262k 14.4 -> 13.5   524k+ worse (the folder kernel wants two CTAs per SM)
+        // Taken only while the shape knobs are at their defaults; an explicit `threads` / `ctas_per_sm` is obeyed.
+        struct Shape
+            {
+            cavb200_handle* h;
+            int threads, ctas;
+            Shape(cavb200_handle* hh) : h(hh), threads(hh->tune.threads), ctas(hh->tune.ctas_per_sm) { }
+            ~Shape()
+                {
+                h->tune.threads = threads;
+                h->tune.ctas_per_sm = ctas;
+                }
+            } keep(h);
+        if (h->tune.threads == 384 && h->tune.ctas_per_sm == 2 && h->tune.auto_threads)
+            {
+            const unsigned long long work = (FORCE ? (unsigned long long)f.N : 0ull) > (BUSSI ? (unsigned long long)b.n : 0ull)
+                                                ? (unsigned long long)f.N
+                                                : (unsigned long long)b.n;
+            int t = 0;
+            if (FORCE && !BUSSI)
+                t = (work >= 32768ull && work < 400000ull) ? 704 : ((work >= 400000ull && work < 2000000ull) ? 768 : 0);
+            else if (!FORCE)
+                t = work < 300000ull ? 512 : 0;
+            else
+                t = (work >= 49152ull && work < 400000ull) ? 512 : 0;
+            if (t)
+                {
+                h->tune.threads = t;
+                h->tune.ctas_per_sm = 1;
+                }
+            }
         if (h->tune.threads <= 384)
             return launch_t<FORCE, BUSSI, 2, 384>(h, f, b, s);
         if (h->tune.threads <= 768) // one 768-thread CTA per SM: same 80-register budget, half the records
             return launch_t<FORCE, BUSSI, 2, 768>(h, f, b, s);
         return launch_t<FORCE, BUSSI, 2, 1024>(h, f, b, s);
+        }
         }
     }
 
