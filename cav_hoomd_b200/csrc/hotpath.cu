@@ -485,15 +485,17 @@ __global__ void __launch_bounds__(1024, 1) k_cluster(ForceIn f, BussiIn b, Scala
 // ------------------------------------------------------------------------------------------
 // LB = launch bound: 1024 caps the kernel at 64 registers/thread (two 512-thread CTAs or one
 // 1024-thread CTA per SM); 512 allows 128 registers for one 512-thread CTA per SM.
+// `shape_threads` / `shape_ctas`: threads per CTA and CTAs per SM of the persistent grids (the tuning knobs, or what
+// launch_u's rule made of them)
 template<bool FORCE, bool BUSSI, int UNROLL, int LB, bool LIST = false>
-static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaStream_t s)
+static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaStream_t s, int shape_threads, int shape_ctas)
     {
     if (BUSSI && !LIST && b.gidx != nullptr)
         {
         // an index list: only the Bussi-only calls take one (cavb200_bussi, cavb200_bussi_ke)
         if (FORCE)
             return (int)cudaErrorInvalidValue;
-        return launch_t<FORCE, BUSSI && !FORCE, UNROLL, LB, !FORCE>(h, f, b, s);
+        return launch_t<FORCE, BUSSI && !FORCE, UNROLL, LB, !FORCE>(h, f, b, s, shape_threads, shape_ctas);
         }
         {
         const unsigned long long work_small = (FORCE ? (unsigned long long)f.N : 0ull) > (BUSSI ? (unsigned long long)b.n : 0ull)
@@ -570,13 +572,13 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
                 }
             }
         }
-    int threads = h->tune.threads;
+    int threads = shape_threads;
     const unsigned long long work = (FORCE ? (unsigned long long)f.N : 0ull) > (BUSSI ? (unsigned long long)b.n : 0ull)
                                         ? (unsigned long long)f.N
                                         : (unsigned long long)b.n;
     // (the Bussi-only call follows the same rule -- 1M: 15.9 us at 384 threads, 15.6 at 352, profiles/threads_r2a.txt;
     // the force-only call is flat in the CTA size)
-    if (BUSSI && UNROLL == 2 && LB == 384 && threads == 384 && h->tune.auto_threads && h->tune.ctas_per_sm == 2)
+    if (BUSSI && UNROLL == 2 && LB == 384 && threads == 384 && h->tune.auto_threads && shape_ctas == 2)
         {
         // Step kernel, default shape: a thread walks ceil(q) particles (q = work / streaming threads) two at a time, so
         // each of its four passes is ceil(ceil(q) / 2) dependent memory round trips.  Among 320 / 352 / 384 threads per
@@ -599,7 +601,7 @@ static int launch_t(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
     unsigned long long want = (work + threads - 1) / threads;
     if (want < 1)
         want = 1;
-    int max_grid = h->num_sms * h->tune.ctas_per_sm;
+    int max_grid = h->num_sms * shape_ctas;
     if (max_grid > MAX_PARTIALS)
         max_grid = MAX_PARTIALS;
     Final* fin_dev = reinterpret_cast<Final*>(h->counters + 8);
@@ -792,11 +794,11 @@ static int launch_u(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
     case 8:
         if (h->tune.threads > 256)
             return (int)cudaErrorInvalidConfiguration;
-        return launch_t<FORCE, BUSSI, 8, 256>(h, f, b, s);
+        return launch_t<FORCE, BUSSI, 8, 256>(h, f, b, s, h->tune.threads, h->tune.ctas_per_sm);
     case 4:
         if (h->tune.threads > 512)
             return (int)cudaErrorInvalidConfiguration;
-        return launch_t<FORCE, BUSSI, 4, 512>(h, f, b, s);
+        return launch_t<FORCE, BUSSI, 4, 512>(h, f, b, s, h->tune.threads, h->tune.ctas_per_sm);
     default:
         {
         // two 384-thread CTAs per SM (24 warps, 80 registers): the shape that keeps the fused
@@ -809,18 +811,8 @@ static int launch_u(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
         //   Bussi call   16k 5.3 -> 4.0    65k 5.1 -> 4.1     131k 5.2 -> 4.8     262k 6.3 -> 6.2     400k+ no better or worse
         //   step         65k 9.6 -> 9.3    131k 13.1 -> 11.3  262k 14.4 -> 13.5   524k+ worse (the folder kernel wants two CTAs per SM)
         // Taken only while the shape knobs are at their defaults; an explicit `threads` / `ctas_per_sm` is obeyed.
-        struct Shape
-            {
-            cavb200_handle* h;
-            int threads, ctas;
-            Shape(cavb200_handle* hh) : h(hh), threads(hh->tune.threads), ctas(hh->tune.ctas_per_sm) { }
-            ~Shape()
-                {
-                h->tune.threads = threads;
-                h->tune.ctas_per_sm = ctas;
-                }
-            } keep(h);
-        if (h->tune.threads == 384 && h->tune.ctas_per_sm == 2 && h->tune.auto_threads)
+        int threads = h->tune.threads, ctas = h->tune.ctas_per_sm;
+        if (threads == 384 && ctas == 2 && h->tune.auto_threads)
             {
             const unsigned long long work = (FORCE ? (unsigned long long)f.N : 0ull) > (BUSSI ? (unsigned long long)b.n : 0ull)
                                                 ? (unsigned long long)f.N
@@ -834,15 +826,15 @@ static int launch_u(cavb200_handle* h, const ForceIn& f, const BussiIn& b, cudaS
                 t = (work >= 49152ull && work < 400000ull) ? 512 : 0;
             if (t)
                 {
-                h->tune.threads = t;
-                h->tune.ctas_per_sm = 1;
+                threads = t;
+                ctas = 1;
                 }
             }
-        if (h->tune.threads <= 384)
-            return launch_t<FORCE, BUSSI, 2, 384>(h, f, b, s);
-        if (h->tune.threads <= 768) // one 768-thread CTA per SM: same 80-register budget, half the records
-            return launch_t<FORCE, BUSSI, 2, 768>(h, f, b, s);
-        return launch_t<FORCE, BUSSI, 2, 1024>(h, f, b, s);
+        if (threads <= 384)
+            return launch_t<FORCE, BUSSI, 2, 384>(h, f, b, s, threads, ctas);
+        if (threads <= 768) // one 768-thread CTA per SM: same 80-register budget, half the records
+            return launch_t<FORCE, BUSSI, 2, 768>(h, f, b, s, threads, ctas);
+        return launch_t<FORCE, BUSSI, 2, 1024>(h, f, b, s, threads, ctas);
         }
         }
     }
