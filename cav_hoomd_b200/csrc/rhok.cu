@@ -49,10 +49,11 @@ __constant__ double SC[18] = {
     -1.38888888888741095749e-03, // 14 C2
     4.16666666666666019037e-02,  // 15 C1
     -0.5, 1.0};
-__device__ __forceinline__ void sincos_lean(double x, double& s, double& c)
+// sin and cos of the REDUCED argument r = x - q pi/2 and the quadrant count q (two's complement, only q & 3 matters)
+__device__ __forceinline__ void sincos_reduced(double x, double& sr, double& cr, int& q)
     {
     const double t = __fma_rn(x, SC[1], SC[0]);
-    const int q = __double2loint(t);
+    q = __double2loint(t);
     const double n = __dadd_rn(t, -SC[0]);
     double r = __fma_rn(-n, SC[2], x);
     r = __fma_rn(-n, SC[3], r);
@@ -62,13 +63,19 @@ __device__ __forceinline__ void sincos_lean(double x, double& s, double& c)
     ps = __fma_rn(z, ps, SC[7]);
     ps = __fma_rn(z, ps, SC[8]);
     ps = __fma_rn(z, ps, SC[9]);
-    const double sr = __fma_rn(__dmul_rn(r, z), ps, r);
+    sr = __fma_rn(__dmul_rn(r, z), ps, r);
     double pc = __fma_rn(z, SC[10], SC[11]);
     pc = __fma_rn(z, pc, SC[12]);
     pc = __fma_rn(z, pc, SC[13]);
     pc = __fma_rn(z, pc, SC[14]);
     pc = __fma_rn(z, pc, SC[15]);
-    const double cr = __fma_rn(__dmul_rn(z, z), pc, __fma_rn(z, SC[16], SC[17]));
+    cr = __fma_rn(__dmul_rn(z, z), pc, __fma_rn(z, SC[16], SC[17]));
+    }
+__device__ __forceinline__ void sincos_lean(double x, double& s, double& c)
+    {
+    double sr, cr;
+    int q;
+    sincos_reduced(x, sr, cr, q);
     // quadrant q & 3:  0: (s, c) = (sr, cr)   1: (cr, -sr)   2: (-sr, -cr)   3: (-cr, sr)
     const bool odd = q & 1;
     const double ss = odd ? cr : sr;
@@ -77,6 +84,66 @@ __device__ __forceinline__ void sincos_lean(double x, double& s, double& c)
     const int fc = ((q + 1) & 2) << 30; // sign flip of cos in quadrants 1, 2
     s = __hiloint2double(__double2hiint(ss) ^ fs, __double2loint(ss));
     c = __hiloint2double(__double2hiint(cc) ^ fc, __double2loint(cc));
+    }
+
+__device__ __forceinline__ unsigned int abs_hi(double v) { return (unsigned int)__double2hiint(v) & 0x7fffffffu; }
+
+// One thread's walk over a staged tile: particles pg, pg + groups, ... against its KB wave vectors.
+// CHECK = false: the caller has bounded every |k.r| of the tile below 2^20, so the inner loop carries no range test
+// (2-3 integer instructions per (particle, k) pair that share the issue port with the half-rate FP64 pipe).
+// The quadrant fix-up of a pair costs ten integer / select instructions (swap sin and cos: 4 FSEL; two sign flips; the
+// parity predicate), and every one of them takes an issue slot the half-rate FP64 pipe could have used.  Instead the pair
+// is ROTATED by the quadrant with the FP64 pipe itself: (cq, sq) = (cos, sin)(q pi/2) in {0, +-1} comes out of a four-entry
+// shared-memory table, and  re += cr cq - sr sq,  im += sr cq + cr sq  as four FMAs in place of the two additions.  One
+// product of each line is an exact zero, so the sums are bit for bit what the swap-and-flip gave.
+template<int KB, bool CHECK>
+__device__ __forceinline__ void rhok_walk(const double* sx, const double* sy, const double* sz, const double2* rot, uint32_t pg,
+                                          uint32_t n, uint32_t groups, const double (&kx)[KB], const double (&ky)[KB],
+                                          const double (&kz)[KB], double (&re)[KB], double (&im)[KB])
+    {
+    for (uint32_t j = pg; j < n; j += groups)
+        {
+        const double x = sx[j], y = sy[j], z = sz[j];
+        double kr[KB];
+        bool huge = false;
+#pragma unroll
+        for (int m = 0; m < KB; m++)
+            {
+            // analysis.py:42 np.dot(positions, k_vec) = x kx + y ky + z kz (NumPy hands this to a BLAS
+            // gemv, which contracts to FMAs on any AVX2 host; so does this)
+            kr[m] = __fma_rn(z, kz[m], __fma_rn(y, ky[m], __dmul_rn(x, kx[m])));
+            // |kr| >= 2^20, inf or nan: exponent test on the integer pipe (DSETP would sit on the FP64 pipe)
+            if (CHECK)
+                huge = huge || (__double2hiint(kr[m]) & 0x7fffffff) >= 0x41300000;
+            }
+        if (!CHECK || !huge)
+            {
+            // one basic block for the KB independent chains: coefficients are fetched once
+            // (written stage by stage over the KB arguments instead -- every dependent pair 2 KB instructions apart in
+            // program order -- ptxas interleaves three or four chains instead of two or three, needs 40 B of spills
+            // and the frame takes 0.1277 ms instead of 0.1256: not what limits the FP64 pipe at 70 %)
+#pragma unroll
+            for (int m = 0; m < KB; m++)
+                {
+                double sr, cr;
+                int q;
+                sincos_reduced(kr[m], sr, cr, q);
+                const double2 w = rot[q & 3];
+                re[m] = __fma_rn(-sr, w.y, __fma_rn(cr, w.x, re[m]));
+                im[m] = __fma_rn(cr, w.y, __fma_rn(sr, w.x, im[m]));
+                }
+            }
+        else
+            {
+            for (int m = 0; m < KB; m++)
+                {
+                double sn, cs;
+                sincos(kr[m], &sn, &cs); // huge arguments (and inf/nan): the library's Payne-Hanek path
+                re[m] += cs;
+                im[m] += sn;
+                }
+            }
+        }
     }
 
 // grid (P, T); thread (pg, kq): particle group pg walks the tile with stride `groups`, kq owns KB
@@ -89,6 +156,8 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
            int direct)
     {
     __shared__ double sx[RHOK_TILE], sy[RHOK_TILE], sz[RHOK_TILE];
+    __shared__ unsigned int tile_maxhi[2]; // largest hi word of |coordinate| in the tile being staged (by tile parity)
+    __shared__ double2 rot[4];             // (cos, sin)(q pi/2), q = 0..3
     extern __shared__ double sred[]; // [groups][KQ * KB][2]
 
     const uint32_t t = blockIdx.y, p = blockIdx.x;
@@ -109,6 +178,14 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
         kz[m] = in ? __ldg(kvec + 3 * (k0 + k) + 2) : 0.0;
         re[m] = im[m] = 0.0;
         }
+    double kbound = 0.0; // max over this thread's wave vectors of |kx| + |ky| + |kz| >= |k.r| / max|coordinate|
+#pragma unroll
+    for (int m = 0; m < KB; m++)
+        kbound = fmax(kbound, fabs(kx[m]) + fabs(ky[m]) + fabs(kz[m]));
+    if (tid < 2)
+        tile_maxhi[tid] = 0u;
+    if (tid < 4)
+        rot[tid] = make_double2(tid == 0 ? 1.0 : (tid == 2 ? -1.0 : 0.0), tid == 1 ? 1.0 : (tid == 3 ? -1.0 : 0.0));
 
     // contiguous slice of this frame, in whole tiles
     const uint32_t tiles = (N + RHOK_TILE - 1) / RHOK_TILE;
@@ -122,6 +199,7 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
         const uint32_t base = tile * RHOK_TILE;
         const uint32_t n = min((uint32_t)RHOK_TILE, N - base);
         __syncthreads();
+        unsigned int mx = 0u; // largest hi word of |coordinate| this thread stages
         if (stride == 4)
             {
             const double4* src = reinterpret_cast<const double4*>(frame) + base;
@@ -131,6 +209,7 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
                 sx[j] = r.x;
                 sy[j] = r.y;
                 sz[j] = r.z;
+                mx = max(mx, max(max(abs_hi(r.x), abs_hi(r.y)), abs_hi(r.z)));
                 }
             }
         else if (stride == RHOK_F32)
@@ -142,6 +221,7 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
                 const double v = (double)__ldg(src + e);
                 const uint32_t j = e / 3, c = e - 3 * j;
                 (c == 0 ? sx : (c == 1 ? sy : sz))[j] = v;
+                mx = max(mx, abs_hi(v));
                 }
             }
         else
@@ -152,51 +232,25 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
                 const double v = __ldg(src + e);
                 const uint32_t j = e / 3, c = e - 3 * j;
                 (c == 0 ? sx : (c == 1 ? sy : sz))[j] = v;
+                mx = max(mx, abs_hi(v));
                 }
             }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((tid & 31u) == 0)
+            atomicMax(&tile_maxhi[tile & 1u], mx);
         __syncthreads();
+        // upper bound of |coordinate| over the tile (hi word + 1, lo word 0 bounds every double with that hi word); with
+        // the thread's own bound on |kx| + |ky| + |kz| it decides once per tile whether any argument can reach 2^20
+        const unsigned int mh = tile_maxhi[tile & 1u];
+        if (tid == 0)
+            tile_maxhi[(tile + 1u) & 1u] = 0u;
+        const bool fast = mh < 0x7ff00000u && __dmul_rn(kbound, __hiloint2double((int)(mh + 1u), 0)) < 1048575.0;
         if (active)
             {
-            for (uint32_t j = pg; j < n; j += groups)
-                {
-                const double x = sx[j], y = sy[j], z = sz[j];
-                double kr[KB];
-                bool huge = false;
-#pragma unroll
-                for (int m = 0; m < KB; m++)
-                    {
-                    // analysis.py:42 np.dot(positions, k_vec) = x kx + y ky + z kz (NumPy hands this to a BLAS
-                    // gemv, which contracts to FMAs on any AVX2 host; so does this)
-                    kr[m] = __fma_rn(z, kz[m], __fma_rn(y, ky[m], __dmul_rn(x, kx[m])));
-                    // |kr| >= 2^20, inf or nan: exponent test on the integer pipe (DSETP would sit on the FP64 pipe)
-                    huge = huge || (__double2hiint(kr[m]) & 0x7fffffff) >= 0x41300000;
-                    }
-                if (!huge)
-                    {
-                    // one basic block for the KB independent chains: coefficients are fetched once
-                    // (written stage by stage over the KB arguments instead -- every dependent pair 2 KB instructions apart in
-                    // program order -- ptxas interleaves three or four chains instead of two or three, needs 40 B of spills
-                    // and the frame takes 0.1277 ms instead of 0.1256: not what limits the FP64 pipe at 70 %)
-#pragma unroll
-                    for (int m = 0; m < KB; m++)
-                        {
-                        double sn, cs;
-                        sincos_lean(kr[m], sn, cs);
-                        re[m] += cs;
-                        im[m] += sn;
-                        }
-                    }
-                else
-                    {
-                    for (int m = 0; m < KB; m++)
-                        {
-                        double sn, cs;
-                        sincos(kr[m], &sn, &cs); // huge arguments (and inf/nan): the library's Payne-Hanek path
-                        re[m] += cs;
-                        im[m] += sn;
-                        }
-                    }
-                }
+            if (fast)
+                rhok_walk<KB, false>(sx, sy, sz, rot, pg, n, groups, kx, ky, kz, re, im);
+            else
+                rhok_walk<KB, true>(sx, sy, sz, rot, pg, n, groups, kx, ky, kz, re, im);
             }
         }
 

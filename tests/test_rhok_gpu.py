@@ -161,3 +161,25 @@ def test_rhok_nonfinite_positions_propagate(handle):
     with np.errstate(invalid="ignore"):
         ref = O.numpy_density_field(frames[0], kvec)
     assert np.array_equal(np.isnan(rho[0].real), np.isnan(ref.real)) and np.isnan(rho[0].real).any()
+
+
+def test_sincos_accuracy_per_argument(handle):
+    """One particle per frame makes rho[t][k] = (cos, sin)(k . r_t): 64 x 1024 arguments spread over |k.r| < 2^19, each
+    against long-double truth of the SAME rounded argument.  The kernel's own reduction and polynomials (rhok.cu
+    sincos_reduced, the quadrant rotation) must stay within 1 ulp of the result's binade -- absolute 2.3e-16 -- for
+    every one of them."""
+    rng = np.random.default_rng(5)
+    T, K = 1024, 64
+    frames = np.zeros((T, 1, 3))
+    frames[:, 0, 0] = rng.uniform(-1.0, 1.0, T) * 10.0 ** rng.uniform(-3, 5.7, T)
+    kvec = np.zeros((K, 3))
+    kvec[:, 0] = rng.uniform(0.5, 1.0, K)
+    d_rho = capi.DeviceArray((T, K, 2), np.float64)
+    handle.rhok(capi.DeviceArray.from_numpy(frames), 3, 3, 1, T, capi.DeviceArray.from_numpy(kvec), K, d_rho)
+    rho = d_rho.numpy()
+    arg = frames[:, 0, 0][:, None] * kvec[:, 0][None, :]  # one multiplication, rounded once, as in the kernel
+    assert np.abs(arg).max() < 2.0 ** 19 and np.abs(arg).max() > 1e5
+    la = arg.astype(np.longdouble)
+    err_c = np.abs(rho[..., 0].astype(np.longdouble) - np.cos(la)).max()
+    err_s = np.abs(rho[..., 1].astype(np.longdouble) - np.sin(la)).max()
+    assert float(err_c) <= 2.3e-16 and float(err_s) <= 2.3e-16, (float(err_c), float(err_s))
