@@ -446,7 +446,7 @@ def leg_fkt(cx, n_mol):
     flops; the kernel issues 27: its accumulates are four FMAs that rotate by the quadrant) -- against the DFMA rate of
     this device measured by cavb200_debug_fp64_peak in this run."""
     capi, h, st = cx.capi, cx.h, cx.st
-    N, K, T, ORIGINS = n_mol + 1, 64, 8, 1000
+    N, K, T, ORIGINS = n_mol + 1, 64, 32, 1000
     FP64_PER_PAIR, FLOPS_PER_PAIR = 26, 44
     base = synth.make_system(n_mol, replica=cx.rank)
     rng = np.random.default_rng(7 + cx.rank)
@@ -457,7 +457,7 @@ def leg_fkt(cx, n_mol):
     for t in range(T):
         cur[:, :3] += 0.05 * rng.standard_normal((N, 3))  # random walk, sigma 0.05 Bohr
         frames[t] = cur
-    bufs = [capi.DeviceArray.from_numpy(frames) for _ in range(2)]  # 2 x 256 MB
+    bufs = [capi.DeviceArray.from_numpy(frames) for _ in range(2)]  # 2 x 1 GB
     d_rho = capi.DeviceArray((T, K, 2), np.float64)
 
     def launch(k):
@@ -466,10 +466,10 @@ def leg_fkt(cx, n_mol):
     for k in range(3):
         launch(k)
     capi.sync()
-    # one GPU: 8 launches (64 frames); N GPUs: the 1000 frames in blocks of T round-robin over the ranks
+    # one GPU: 4 launches (128 frames); N GPUs: the 1000 frames in blocks of T round-robin over the ranks
     # (replicas.frames_for_rank), no data-path collective, time = max over ranks
     from cav_hoomd_b200 import replicas
-    n_launch = 8 if cx.world == 1 else len(replicas.frames_for_rank(ORIGINS, cx.rank, cx.world, block=T))
+    n_launch = 4 if cx.world == 1 else len(replicas.frames_for_rank(ORIGINS, cx.rank, cx.world, block=T))
     ms, launches = cx.timed(launch, n_launch, gate=True)
     frames_done = n_launch * T if cx.world == 1 else ORIGINS
     ms_per_frame = ms / frames_done

@@ -224,6 +224,7 @@ static int* tuning_slot(cavb::Tuning* t, const char* key)
     if (!strcmp(key, "small_n")) return &t->small_n;
     if (!strcmp(key, "cluster_n")) return &t->cluster_n;
     if (!strcmp(key, "cluster_ctas")) return &t->cluster_ctas;
+    if (!strcmp(key, "rhok_threads")) return &t->rhok_threads;
     return nullptr;
     }
 

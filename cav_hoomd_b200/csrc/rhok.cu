@@ -18,6 +18,11 @@ namespace cavb
 #ifndef RHOK_MIN_CTAS
 #define RHOK_MIN_CTAS 2
 #endif
+
+#ifndef RHOK_KB
+#define RHOK_KB 4
+#endif
+constexpr int RHOK_KB_HOST = RHOK_KB;
 constexpr int RHOK_TILE = 1024; // particles per shared-memory tile (24 KB)
 constexpr uint32_t RHOK_F32 = 13;  // internal `stride` code: float32 xyz positions (frame_stride then counts floats)
 
@@ -355,7 +360,12 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
         CAVB_CHECK(cudaMemsetAsync(rho, 0, sizeof(double) * 2ull * K * T, s));
         return 0;
         }
-    const int threads = 256;
+    // 128-thread CTAs (four per SM) when every k-quad still gets at least four particle groups: a CTA that is staging
+    // its next tile then idles a quarter of the SM's warps instead of half (8 frames per launch: 0.1239 -> 0.1213 ms per
+    // frame; 64 frames: equal).  192 threads: worse (0.143).
+    const int threads = (h->tune.rhok_threads == 128 || h->tune.rhok_threads == 256)
+                            ? h->tune.rhok_threads
+                            : ((K + RHOK_KB_HOST - 1) / RHOK_KB_HOST <= 32 ? 128 : 256);
     const uint32_t tiles = (N + RHOK_TILE - 1) / RHOK_TILE;
     uint32_t P = (24u * (uint32_t)h->num_sms + T - 1) / T;
     if (P > tiles)

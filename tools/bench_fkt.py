@@ -38,6 +38,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("gloo")
     h = capi.Handle(local)
+    if os.environ.get("RHOK_THREADS"):
+        h.set_tuning(rhok_threads=int(os.environ["RHOK_THREADS"]))
     s = synth.make_system(args.n)
     rng = np.random.default_rng(7)
     kvec = synth.fibonacci_sphere(K) * 1.0
