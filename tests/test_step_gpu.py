@@ -415,3 +415,40 @@ def test_cluster_kernel_back_to_back_launches_of_different_shapes():
         assert h.fault_count == 0
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("n_mol", [40000, 131072, 350000, 500000, 1200000])
+def test_launch_shape_rule_changes_nothing_but_the_partition(coracle, n_mol):
+    """Below ~2M particles the launcher picks one CTA per SM for some calls (hotpath.cu launch_u: force call 704 / 768
+    threads, Bussi call and step 512); an explicit `threads` switches the rule off.  Force call, Bussi call and the
+    one-launch step under the rule and under two 384-thread CTAs per SM: same photon, forces / energies / alpha to
+    1e-14 of each other (another partition of the same compensated sums), and the rule's results against the oracle."""
+    s = synth.make_system(n_mol, replica=7)
+    a = args_for(n_mol)
+    p = capi.Params.make(0.01, 1e-3)
+    res = {}
+    for rule in (True, False):
+        h = capi.Handle(0)
+        try:
+            if not rule:
+                h.set_tuning(threads=384)
+            step = run_step(h, s, 0, n_mol, a)
+            dev = {k: capi.DeviceArray.from_numpy(getattr(s, k)) for k in ("pos", "charge", "image", "vel")}
+            d_f = capi.DeviceArray.from_numpy(np.full((s.N, 4), np.nan))
+            h.bussi_reset()
+            h.force(dev["pos"], dev["charge"], dev["image"], d_f, s.N, s.box, s.L_typeid, p)
+            h.bussi(dev["vel"], None, 0, n_mol, a)
+            res[rule] = (step, d_f.numpy(), dev["vel"].numpy(), h.force_read(), h.bussi_read())
+            assert h.fault_count == 0
+        finally:
+            h.close()
+    check_against_oracle(coracle, s, 0, n_mol, a, res[True][0])
+    (st1, f1, v1, fr1, b1), (st0, f0, v0, fr0, b0) = res[True], res[False]
+    scale = np.abs(f0).max()
+    assert fr1[2] == fr0[2] == st1[4] == st0[4]
+    assert np.abs(f1 - f0).max() <= 1e-14 * scale and np.abs(st1[0] - st0[0]).max() <= 1e-14 * scale
+    assert np.allclose(fr1[0], fr0[0], rtol=1e-13, atol=0) and np.allclose(st1[2], st0[2], rtol=1e-13, atol=0)
+    assert abs(b1["alpha"] - b0["alpha"]) <= 1e-14 and abs(st1[5]["alpha"] - st0[5]["alpha"]) <= 1e-14
+    assert np.allclose(v1, v0, rtol=1e-14, atol=0) and np.allclose(st1[1], st0[1], rtol=1e-14, atol=0)
+    # the two calls against the one launch, under the rule: force call and step take different shapes in places
+    assert np.abs(f1 - st1[0]).max() <= 1e-14 * scale and np.allclose(v1, st1[1], rtol=1e-14, atol=0)
