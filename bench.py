@@ -441,13 +441,13 @@ class Ctx:
 def leg_fkt(cx, n_mol):
     """BASELINE configs[4]: F(k,t) on a 1M-particle trajectory, 64 wave vectors, 1000 time origins.
     rho[t][k] = sum_j exp(i k.r_j(t)) for T frames per launch (two rotating frame buffers, larger than L2), then the
-    1000 x 1000 origin/lag table.  Roofline: the kernel is FP64-pipe bound -- 26 algorithmic FP64
-    instructions per (particle, k) pair (3 for k.r, 21 for sin and cos, 2 accumulates; 18 of them fused multiply-adds = 44
-    flops; the kernel issues 27: its accumulates are four FMAs that rotate by the quadrant) -- against the DFMA rate of
-    this device measured by cavb200_debug_fp64_peak in this run."""
+    1000 x 1000 origin/lag table.  Roofline: the kernel is FP64-pipe bound -- 17 FP64 instructions per
+    (particle, k) pair (3 for k.r, 4 for the reduction to |r| <= pi/512, 6 for sin r and cos r, 4 FMAs that rotate by the
+    table entry and accumulate; 13 of them fused multiply-adds = 30 flops) -- against the DFMA rate of this device measured
+    by cavb200_debug_fp64_peak in this run."""
     capi, h, st = cx.capi, cx.h, cx.st
     N, K, T, ORIGINS = n_mol + 1, 64, 32, 1000
-    FP64_PER_PAIR, FLOPS_PER_PAIR = 26, 44
+    FP64_PER_PAIR, FLOPS_PER_PAIR = 17, 30
     base = synth.make_system(n_mol, replica=cx.rank)
     rng = np.random.default_rng(7 + cx.rank)
     kvec = synth.fibonacci_sphere(K) * 1.0
@@ -494,7 +494,7 @@ def leg_fkt(cx, n_mol):
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved / peak_tflops, "traffic": None, "kernel": "k_rhok<4>",
                      "convention": f"FP64-pipe issue slots, counted as fused multiply-adds (2 flops each): {FP64_PER_PAIR} "
-                                   f"algorithmic FP64 instructions per (particle, k) pair (the kernel issues 27); arithmetic flops are {FLOPS_PER_PAIR} per pair",
+                                   f"FP64 instructions per (particle, k) pair (3 for k.r, 4 reduction to |r| <= pi/512, 6 for sin r and cos r, 4 rotate-by-table-entry-and-accumulate; round 1 and early round 2 needed 26); arithmetic flops are {FLOPS_PER_PAIR} per pair",
                      "arithmetic_TFLOPs": FLOPS_PER_PAIR * pairs_per_s / cx.world / 1e12,
                      "peak_source": "measured in this run: cavb200_debug_fp64_peak (DFMA microbenchmark, "
                                     "cav_hoomd_b200/csrc/debug.cu), best of 4"},

@@ -193,6 +193,7 @@ int cavb200_destroy(cavb200_handle* h)
     cudaFree(h->counters);
     cudaFree(h->stamps);
     cudaFree(h->rhok_partials);
+    cudaFree(h->rhok_table);
     if (h->fault_host)
         cudaFreeHost(h->fault_host);
     free(h);

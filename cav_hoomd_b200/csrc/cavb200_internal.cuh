@@ -146,6 +146,7 @@ struct cavb200_handle
     // F(k,t) workspace
     double* rhok_partials;
     uint64_t rhok_partials_bytes;
+    void* rhok_table; // device, (cos, sin)(2 pi e / 512) as double2 (rhok.cu)
     };
 
 namespace cavb

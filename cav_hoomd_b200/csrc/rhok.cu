@@ -26,69 +26,43 @@ constexpr int RHOK_KB_HOST = RHOK_KB;
 constexpr int RHOK_TILE = 1024; // particles per shared-memory tile (24 KB)
 constexpr uint32_t RHOK_F32 = 13;  // internal `stride` code: float32 xyz positions (frame_stride then counts floats)
 
-// sin and cos of one argument, |x| < 2^20, both to < 1 ulp-ish (abs. error ~2e-16).
-// The library sincos() costs ~70 issue slots per call here, two thirds of them integer/selection/slow-path
-// plumbing, and `ncu` showed the first kernel issue-bound (88 % issue slots busy, FP64 pipe at 50 %,
-// profiles/ncu_rhok_r1a_summary.txt).  This one is 21 FP64 instructions and ~8 integer ones:
-//   n = rint(x * 2/pi) by the 1.5*2^52 trick;  r = x - n*pio2_hi - n*pio2_lo with two FMAs (n*pio2_hi is
-//   exact inside the FMA for |n| < 2^20);  fdlibm's __kernel_sin/__kernel_cos minimax polynomials on
-//   [-pi/4, pi/4] (public-domain constants, < 1 ulp);  quadrant fix-up by swapping and flipping sign bits.
-// (the constants sit in constant memory so that every DFMA takes its coefficient as a c[bank][offset]
-// operand; as literals the compiler rebuilt each one with two UMOVs inside the loop -- 25 extra issue
-// slots per pair)
-__constant__ double SC[18] = {
-    6755399441055744.0,          // 0  1.5 * 2^52
-    6.36619772367581382433e-01,  // 1  2/pi
-    1.57079632679489655800e+00,  // 2  pi/2 hi
-    6.12323399573676603587e-17,  // 3  pi/2 lo
-    1.58969099521155010221e-10,  // 4  S6
-    -2.50507602534068634195e-08, // 5  S5
-    2.75573137070700676789e-06,  // 6  S4
-    -1.98412698298579493134e-04, // 7  S3
-    8.33333333332248946124e-03,  // 8  S2
-    -1.66666666666666324348e-01, // 9  S1
-    -1.13596475577881948265e-11, // 10 C6
-    2.08757232129817482790e-09,  // 11 C5
-    -2.75573143513906633035e-07, // 12 C4
-    2.48015872894767294178e-05,  // 13 C3
-    -1.38888888888741095749e-03, // 14 C2
-    4.16666666666666019037e-02,  // 15 C1
+// exp(i x) for |x| < 2^20 by table and short polynomial, both components to ~1 ulp of 1 (abs. error <= 2.4e-16).
+// History: the library sincos() cost ~70 issue slots per call and left the kernel issue bound; an inline
+// quadrant reduction with fdlibm's degree-13/14 polynomials brought a (particle, k) pair to 27 FP64 instructions and the
+// FP64 pipe to 79 % busy -- from there the only way down is fewer FP64 instructions.  Now:
+//   n = rint(x * 512/2pi) by the 1.5*2^52 trick;  r = x - n*(2pi/512) with a two-FMA Cody-Waite reduction, |r| <= pi/512;
+//   (C, S) = (cos, sin)(2pi (n mod 512)/512) from a 512-entry table (host long double, rounded once, built by octant
+//   symmetry so the axes are exact);  sin r = r - r^3/6 + r^5/120 (truncation 1e-17 relative),  cos r = 1 - z/2 + c4 z^2
+//   with c4 shifted off 1/24 so the dropped z^3/720 is spread over [0, (pi/512)^2] (2e-17 absolute);  and the rotation
+//   re += c C - s S,  im += c S + s C  is the accumulate itself: 17 FP64 instructions per pair instead of 27, and the ten
+//   integer / select instructions of a quadrant fix-up are one mask and one address.
+// The table sits in shared memory EIGHT times, interleaved by 16 bytes: lane l reads copy l & 7, so the eight lanes of a
+// quarter warp -- the unit a 128-bit shared load is served in -- hit eight different bank groups whatever their entries
+// are: one conflict-free LDS.128 per pair (four wavefronts) where a single copy would serialise ~2.5-fold and make the
+// shared-memory pipe, not the FP64 pipe, the limit.
+// (the constants sit in constant memory so that every DFMA takes its coefficient as a c[bank][offset] operand)
+constexpr int RHOK_TAB = 512;  // table entries over one turn
+constexpr int RHOK_REP = 8;    // interleaved copies
+__constant__ double SC[9] = {
+    6755399441055744.0,                       // 0  1.5 * 2^52
+    6.36619772367581382433e-01 * 128.0,       // 1  512 / 2pi   (fl(2/pi) * 2^7, exact scaling)
+    1.57079632679489655800e+00 / 128.0,       // 2  2pi/512 hi  (fl(pi/2) * 2^-7)
+    6.12323399573676603587e-17 / 128.0,       // 3  2pi/512 lo
+    8.33333333333333333333e-03,               // 4  1/120
+    -1.66666666666666666667e-01,              // 5  -1/6
+    4.16666666666666666667e-02 - 0.8 * 3.764955292163604e-05 / 720.0, // 6  1/24 - 0.8 (pi/512)^2 / 720
     -0.5, 1.0};
-// sin and cos of the REDUCED argument r = x - q pi/2 and the quadrant count q (two's complement, only q & 3 matters)
-__device__ __forceinline__ void sincos_reduced(double x, double& sr, double& cr, int& q)
+// sin and cos of the REDUCED argument r = x - n 2pi/512 and the turn count n (two's complement, only n & 511 matters)
+__device__ __forceinline__ void sincos_reduced(double x, double& sr, double& cr, int& n)
     {
     const double t = __fma_rn(x, SC[1], SC[0]);
-    q = __double2loint(t);
-    const double n = __dadd_rn(t, -SC[0]);
-    double r = __fma_rn(-n, SC[2], x);
-    r = __fma_rn(-n, SC[3], r);
+    n = __double2loint(t);
+    const double nf = __dadd_rn(t, -SC[0]);
+    double r = __fma_rn(-nf, SC[2], x);
+    r = __fma_rn(-nf, SC[3], r);
     const double z = __dmul_rn(r, r);
-    double ps = __fma_rn(z, SC[4], SC[5]);
-    ps = __fma_rn(z, ps, SC[6]);
-    ps = __fma_rn(z, ps, SC[7]);
-    ps = __fma_rn(z, ps, SC[8]);
-    ps = __fma_rn(z, ps, SC[9]);
-    sr = __fma_rn(__dmul_rn(r, z), ps, r);
-    double pc = __fma_rn(z, SC[10], SC[11]);
-    pc = __fma_rn(z, pc, SC[12]);
-    pc = __fma_rn(z, pc, SC[13]);
-    pc = __fma_rn(z, pc, SC[14]);
-    pc = __fma_rn(z, pc, SC[15]);
-    cr = __fma_rn(__dmul_rn(z, z), pc, __fma_rn(z, SC[16], SC[17]));
-    }
-__device__ __forceinline__ void sincos_lean(double x, double& s, double& c)
-    {
-    double sr, cr;
-    int q;
-    sincos_reduced(x, sr, cr, q);
-    // quadrant q & 3:  0: (s, c) = (sr, cr)   1: (cr, -sr)   2: (-sr, -cr)   3: (-cr, sr)
-    const bool odd = q & 1;
-    const double ss = odd ? cr : sr;
-    const double cc = odd ? sr : cr;
-    const int fs = (q & 2) << 30;       // sign flip of sin in quadrants 2, 3
-    const int fc = ((q + 1) & 2) << 30; // sign flip of cos in quadrants 1, 2
-    s = __hiloint2double(__double2hiint(ss) ^ fs, __double2loint(ss));
-    c = __hiloint2double(__double2hiint(cc) ^ fc, __double2loint(cc));
+    sr = __fma_rn(__dmul_rn(r, z), __fma_rn(z, SC[4], SC[5]), r);
+    cr = __fma_rn(z, __fma_rn(z, SC[6], SC[7]), SC[8]);
     }
 
 __device__ __forceinline__ unsigned int abs_hi(double v) { return (unsigned int)__double2hiint(v) & 0x7fffffffu; }
@@ -96,13 +70,9 @@ __device__ __forceinline__ unsigned int abs_hi(double v) { return (unsigned int)
 // One thread's walk over a staged tile: particles pg, pg + groups, ... against its KB wave vectors.
 // CHECK = false: the caller has bounded every |k.r| of the tile below 2^20, so the inner loop carries no range test
 // (2-3 integer instructions per (particle, k) pair that share the issue port with the half-rate FP64 pipe).
-// The quadrant fix-up of a pair costs ten integer / select instructions (swap sin and cos: 4 FSEL; two sign flips; the
-// parity predicate), and every one of them takes an issue slot the half-rate FP64 pipe could have used.  Instead the pair
-// is ROTATED by the quadrant with the FP64 pipe itself: (cq, sq) = (cos, sin)(q pi/2) in {0, +-1} comes out of a four-entry
-// shared-memory table, and  re += cr cq - sr sq,  im += sr cq + cr sq  as four FMAs in place of the two additions.  One
-// product of each line is an exact zero, so the sums are bit for bit what the swap-and-flip gave.
+// `tab` is the interleaved table, entry e of copy c at byte (e * RHOK_REP + c) * 16; lane_slot = (lane & 7) * 16.
 template<int KB, bool CHECK>
-__device__ __forceinline__ void rhok_walk(const double* sx, const double* sy, const double* sz, const double2* rot, uint32_t pg,
+__device__ __forceinline__ void rhok_walk(const double* sx, const double* sy, const double* sz, const char* tab, uint32_t lane_slot, uint32_t pg,
                                           uint32_t n, uint32_t groups, const double (&kx)[KB], const double (&ky)[KB],
                                           const double (&kz)[KB], double (&re)[KB], double (&im)[KB])
     {
@@ -133,7 +103,9 @@ __device__ __forceinline__ void rhok_walk(const double* sx, const double* sy, co
                 double sr, cr;
                 int q;
                 sincos_reduced(kr[m], sr, cr, q);
-                const double2 w = rot[q & 3];
+                // byte offset of entry q mod 512, copy lane & 7: one shift, one (and, or), the table base rides in the LDS itself
+                const double2 w = *reinterpret_cast<const double2*>(
+                    tab + ((((uint32_t)q << 7) & ((RHOK_TAB - 1u) << 7)) | lane_slot));
                 re[m] = __fma_rn(-sr, w.y, __fma_rn(cr, w.x, re[m]));
                 im[m] = __fma_rn(cr, w.y, __fma_rn(sr, w.x, im[m]));
                 }
@@ -158,12 +130,12 @@ template<int KB>
 __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
     k_rhok(const double* __restrict__ pos, uint32_t stride, unsigned long long frame_stride, uint32_t N,
            const double* __restrict__ kvec, uint32_t k0, uint32_t Ks, uint32_t K, double* __restrict__ out, uint32_t P,
-           int direct)
+           int direct, const double2* __restrict__ table)
     {
     __shared__ double sx[RHOK_TILE], sy[RHOK_TILE], sz[RHOK_TILE];
     __shared__ unsigned int tile_maxhi[2]; // largest hi word of |coordinate| in the tile being staged (by tile parity)
-    __shared__ double2 rot[4];             // (cos, sin)(q pi/2), q = 0..3
-    extern __shared__ double sred[]; // [groups][KQ * KB][2]
+    extern __shared__ double2 stab[];      // [RHOK_TAB][RHOK_REP] (cos, sin)(2 pi e / RHOK_TAB), then sred
+    double* sred = reinterpret_cast<double*>(stab + RHOK_TAB * RHOK_REP); // [groups][KQ * KB][2]
 
     const uint32_t t = blockIdx.y, p = blockIdx.x;
     const uint32_t tid = threadIdx.x;
@@ -189,8 +161,11 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
         kbound = fmax(kbound, fabs(kx[m]) + fabs(ky[m]) + fabs(kz[m]));
     if (tid < 2)
         tile_maxhi[tid] = 0u;
-    if (tid < 4)
-        rot[tid] = make_double2(tid == 0 ? 1.0 : (tid == 2 ? -1.0 : 0.0), tid == 1 ? 1.0 : (tid == 3 ? -1.0 : 0.0));
+    // every copy of an entry is written by one thread: consecutive threads write consecutive 16-byte slots
+    for (uint32_t e = tid; e < RHOK_TAB * RHOK_REP; e += blockDim.x)
+        stab[e] = __ldg(table + e / RHOK_REP);
+    const char* tab = reinterpret_cast<const char*>(stab);
+    const uint32_t lane_slot = (tid & (RHOK_REP - 1)) * 16u;
 
     // contiguous slice of this frame, in whole tiles
     const uint32_t tiles = (N + RHOK_TILE - 1) / RHOK_TILE;
@@ -253,9 +228,9 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
         if (active)
             {
             if (fast)
-                rhok_walk<KB, false>(sx, sy, sz, rot, pg, n, groups, kx, ky, kz, re, im);
+                rhok_walk<KB, false>(sx, sy, sz, tab, lane_slot, pg, n, groups, kx, ky, kz, re, im);
             else
-                rhok_walk<KB, true>(sx, sy, sz, rot, pg, n, groups, kx, ky, kz, re, im);
+                rhok_walk<KB, true>(sx, sy, sz, tab, lane_slot, pg, n, groups, kx, ky, kz, re, im);
             }
         }
 
@@ -341,6 +316,32 @@ __global__ void k_fkt(const double* __restrict__ rho, uint32_t T, uint32_t K, ui
 
 using namespace cavb;
 
+// (cos, sin)(2 pi e / RHOK_TAB) in long double, rounded once; octant symmetry makes cos^2 + sin^2 symmetric over the turn
+// and the four axis entries exactly (+-1, 0), (0, +-1)
+static void rhok_table_host(double2* tab)
+    {
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    const int Q = RHOK_TAB / 4;
+    for (int e = 0; e < RHOK_TAB; e++)
+        {
+        const int quad = e / Q, j = e % Q;
+        long double c, s;
+        if (j <= Q / 2)
+            {
+            c = cosl(two_pi * j / RHOK_TAB);
+            s = sinl(two_pi * j / RHOK_TAB);
+            }
+        else
+            {
+            c = sinl(two_pi * (Q - j) / RHOK_TAB);
+            s = cosl(two_pi * (Q - j) / RHOK_TAB);
+            }
+        const double cd = (double)c, sd = (double)s;
+        tab[e] = quad == 0 ? make_double2(cd, sd)
+                           : (quad == 1 ? make_double2(-sd, cd) : (quad == 2 ? make_double2(-cd, -sd) : make_double2(sd, -cd)));
+        }
+    }
+
 static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, uint64_t frame_stride, uint32_t N,
                        uint32_t T, const double* kvec, uint32_t K, double* rho, void* stream)
     {
@@ -360,12 +361,19 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
         CAVB_CHECK(cudaMemsetAsync(rho, 0, sizeof(double) * 2ull * K * T, s));
         return 0;
         }
-    // 128-thread CTAs (four per SM) when every k-quad still gets at least four particle groups: a CTA that is staging
-    // its next tile then idles a quarter of the SM's warps instead of half (8 frames per launch: 0.1239 -> 0.1213 ms per
-    // frame; 64 frames: equal).  192 threads: worse (0.143).
-    const int threads = (h->tune.rhok_threads == 128 || h->tune.rhok_threads == 256)
-                            ? h->tune.rhok_threads
-                            : ((K + RHOK_KB_HOST - 1) / RHOK_KB_HOST <= 32 ? 128 : 256);
+    if (!h->rhok_table)
+        {
+        // first call on this handle: the 8 KB table (a blocking copy from pageable memory, like the workspace growth below)
+        double2 host_tab[RHOK_TAB];
+        rhok_table_host(host_tab);
+        CAVB_CHECK(cudaMalloc((void**)&h->rhok_table, sizeof(host_tab)));
+        CAVB_CHECK(cudaMemcpy(h->rhok_table, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice));
+        CAVB_CHECK(cudaFuncSetAttribute(k_rhok<RHOK_KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(double2) * RHOK_TAB * RHOK_REP + sizeof(double) * 2 * 256 * RHOK_KB)));
+        }
+    // two CTAs of 256 threads per SM: the 64 KB table of each leaves no room for four of 128 (which were worth 1-2 % when
+    // the table was four entries: a CTA staging its next tile idled a quarter of the SM's warps instead of half)
+    const int threads = (h->tune.rhok_threads == 128 || h->tune.rhok_threads == 256) ? h->tune.rhok_threads : 256;
     const uint32_t tiles = (N + RHOK_TILE - 1) / RHOK_TILE;
     uint32_t P = (24u * (uint32_t)h->num_sms + T - 1) / T;
     if (P > tiles)
@@ -399,8 +407,9 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
         const uint32_t Ks = (K - k0) < (uint32_t)threads * KB ? (K - k0) : (uint32_t)threads * KB;
         const uint32_t KQ = (Ks + KB - 1) / KB;
         const uint32_t groups = (uint32_t)threads / KQ;
-        const size_t smem = sizeof(double) * 2 * groups * KQ * KB;
-        k_rhok<KB><<<dim3(P, T), threads, smem, s>>>(pos, stride, frame_stride, N, kvec, k0, Ks, K, target, P, direct);
+        const size_t smem = sizeof(double2) * RHOK_TAB * RHOK_REP + sizeof(double) * 2 * groups * KQ * KB;
+        k_rhok<KB><<<dim3(P, T), threads, smem, s>>>(pos, stride, frame_stride, N, kvec, k0, Ks, K, target, P, direct,
+                                                     (const double2*)h->rhok_table);
         CAVB_CHECK(cudaGetLastError());
         h->launches += 1;
         }
