@@ -23,7 +23,7 @@ namespace cavb
 #define RHOK_KB 4
 #endif
 constexpr int RHOK_KB_HOST = RHOK_KB;
-constexpr int RHOK_TILE = 1024; // particles per shared-memory tile (24 KB)
+constexpr int RHOK_TILE = 512;  // particles per shared-memory tile (16 KB as double4; two buffers)
 constexpr uint32_t RHOK_F32 = 13;  // internal `stride` code: float32 xyz positions (frame_stride then counts floats)
 
 // exp(i x) for |x| < 2^20 by table and short polynomial, both components to ~1 ulp of 1 (abs. error <= 2.4e-16).
@@ -72,13 +72,14 @@ __device__ __forceinline__ unsigned int abs_hi(double v) { return (unsigned int)
 // (2-3 integer instructions per (particle, k) pair that share the issue port with the half-rate FP64 pipe).
 // `tab` is the interleaved table, entry e of copy c at byte (e * RHOK_REP + c) * 16; lane_slot = (lane & 7) * 16.
 template<int KB, bool CHECK>
-__device__ __forceinline__ void rhok_walk(const double* sx, const double* sy, const double* sz, const char* tab, uint32_t lane_slot, uint32_t pg,
+__device__ __forceinline__ void rhok_walk(const double4* tile, const char* tab, uint32_t lane_slot, uint32_t pg,
                                           uint32_t n, uint32_t groups, const double (&kx)[KB], const double (&ky)[KB],
                                           const double (&kz)[KB], double (&re)[KB], double (&im)[KB])
     {
     for (uint32_t j = pg; j < n; j += groups)
         {
-        const double x = sx[j], y = sy[j], z = sz[j];
+        const double4 rj = tile[j]; // one broadcast LDS.128 (a warp holds two neighbouring particle groups)
+        const double x = rj.x, y = rj.y, z = rj.z;
         double kr[KB];
         bool huge = false;
 #pragma unroll
@@ -123,19 +124,72 @@ __device__ __forceinline__ void rhok_walk(const double* sx, const double* sy, co
         }
     }
 
+// asynchronous global -> shared copies (LDGSTS): the tile of the NEXT iteration lands while this one is walked
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+    {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+    }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
+    {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned int)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+    }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Stage tile `tile` of a frame into `dst` as double4 {x, y, z, -}.  Double positions (Scalar4 or xyz) are copied
+// asynchronously, 16 or 8 bytes at a time, with no register in between; float32 positions are widened on the way
+// (exactly, as NumPy does in np.dot(f32, f64)) and therefore go through registers, synchronously.
+__device__ __forceinline__ void rhok_stage(double4* dst, const double* pos, uint32_t stride, unsigned long long frame_off,
+                                           uint32_t base, uint32_t n, uint32_t tid, uint32_t nthreads)
+    {
+    if (stride == 4)
+        {
+        const double2* src = reinterpret_cast<const double2*>(pos + frame_off) + 2ull * base;
+        double2* d2 = reinterpret_cast<double2*>(dst);
+        for (uint32_t e = tid; e < 2 * n; e += nthreads)
+            cp_async16(d2 + e, src + e);
+        }
+    else if (stride == RHOK_F32)
+        {
+        const float* src = reinterpret_cast<const float*>(pos) + frame_off + 3ull * base;
+        double* d1 = reinterpret_cast<double*>(dst);
+        for (uint32_t e = tid; e < 3 * n; e += nthreads)
+            {
+            const uint32_t j = e / 3, c = e - 3 * j;
+            d1[4 * j + c] = (double)__ldg(src + e);
+            }
+        }
+    else
+        {
+        const double* src = pos + frame_off + 3ull * base;
+        double* d1 = reinterpret_cast<double*>(dst);
+        for (uint32_t e = tid; e < 3 * n; e += nthreads)
+            {
+            const uint32_t j = e / 3, c = e - 3 * j;
+            cp_async8(d1 + 4 * j + c, src + e);
+            }
+        }
+    cp_async_commit();
+    }
+
 // grid (P, T); thread (pg, kq): particle group pg walks the tile with stride `groups`, kq owns KB
-// consecutive wave vectors whose components and (re, im) accumulators live in registers, so the three
-// shared-memory loads and the loop bookkeeping of a particle are paid once per KB (particle, k) pairs.
+// consecutive wave vectors whose components and (re, im) accumulators live in registers, so the one
+// shared-memory load and the loop bookkeeping of a particle are paid once per KB (particle, k) pairs.
+// Two tile buffers: the copy of tile i+1 is issued before tile i is walked, so no warp ever waits for HBM -- with two
+// CTAs of eight warps per SM, a CTA that stopped to stage its next tile left the FP64 pipe to the other CTA's two warps
+// per scheduler, which cannot keep it busy.
 template<int KB>
 __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
     k_rhok(const double* __restrict__ pos, uint32_t stride, unsigned long long frame_stride, uint32_t N,
            const double* __restrict__ kvec, uint32_t k0, uint32_t Ks, uint32_t K, double* __restrict__ out, uint32_t P,
            int direct, const double2* __restrict__ table)
     {
-    __shared__ double sx[RHOK_TILE], sy[RHOK_TILE], sz[RHOK_TILE];
-    __shared__ unsigned int tile_maxhi[2]; // largest hi word of |coordinate| in the tile being staged (by tile parity)
-    extern __shared__ double2 stab[];      // [RHOK_TAB][RHOK_REP] (cos, sin)(2 pi e / RHOK_TAB), then sred
-    double* sred = reinterpret_cast<double*>(stab + RHOK_TAB * RHOK_REP); // [groups][KQ * KB][2]
+    __shared__ unsigned int tile_maxhi[2]; // largest hi word of |coordinate| in a staged tile (by buffer)
+    extern __shared__ double2 stab[];      // [RHOK_TAB][RHOK_REP] (cos, sin)(2 pi e / RHOK_TAB), then the two tile buffers
+    double4* tiles2 = reinterpret_cast<double4*>(stab + RHOK_TAB * RHOK_REP); // [2][RHOK_TILE]
+    double* sred = reinterpret_cast<double*>(tiles2); // [groups][KQ * KB][2], after the last tile has been walked
 
     const uint32_t t = blockIdx.y, p = blockIdx.x;
     const uint32_t tid = threadIdx.x;
@@ -143,6 +197,16 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
     const uint32_t groups = blockDim.x / KQ;
     const uint32_t kq = tid % KQ, pg = tid / KQ;
     const bool active = pg < groups;
+
+    // contiguous slice of this frame, in whole tiles
+    const uint32_t tiles = (N + RHOK_TILE - 1) / RHOK_TILE;
+    const uint32_t tiles_per = (tiles + P - 1) / P;
+    const uint32_t tile_lo = p * tiles_per;
+    const uint32_t tile_hi = min(tiles, tile_lo + tiles_per);
+    const unsigned long long frame_off = (unsigned long long)t * frame_stride;
+    if (tile_lo < tile_hi)
+        rhok_stage(tiles2, pos, stride, frame_off, tile_lo * RHOK_TILE, min((uint32_t)RHOK_TILE, N - tile_lo * RHOK_TILE), tid,
+                   blockDim.x);
 
     double kx[KB], ky[KB], kz[KB], re[KB], im[KB];
 #pragma unroll
@@ -167,72 +231,41 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
     const char* tab = reinterpret_cast<const char*>(stab);
     const uint32_t lane_slot = (tid & (RHOK_REP - 1)) * 16u;
 
-    // contiguous slice of this frame, in whole tiles
-    const uint32_t tiles = (N + RHOK_TILE - 1) / RHOK_TILE;
-    const uint32_t tiles_per = (tiles + P - 1) / P;
-    const uint32_t tile_lo = p * tiles_per;
-    const uint32_t tile_hi = min(tiles, tile_lo + tiles_per);
-    const double* frame = pos + (unsigned long long)t * frame_stride;
-
     for (uint32_t tile = tile_lo; tile < tile_hi; tile++)
         {
-        const uint32_t base = tile * RHOK_TILE;
-        const uint32_t n = min((uint32_t)RHOK_TILE, N - base);
-        __syncthreads();
-        unsigned int mx = 0u; // largest hi word of |coordinate| this thread stages
-        if (stride == 4)
+        const uint32_t cur = (tile - tile_lo) & 1u;
+        const double4* buf = tiles2 + cur * RHOK_TILE;
+        const uint32_t n = min((uint32_t)RHOK_TILE, N - tile * RHOK_TILE);
+        cp_async_wait_all();
+        __syncthreads(); // this tile has landed (and the table, first time); everyone has left the other buffer
+        if (tile + 1 < tile_hi)
+            rhok_stage(tiles2 + (cur ^ 1u) * RHOK_TILE, pos, stride, frame_off, (tile + 1) * RHOK_TILE,
+                       min((uint32_t)RHOK_TILE, N - (tile + 1) * RHOK_TILE), tid, blockDim.x);
+        unsigned int mx = 0u; // largest hi word of |coordinate| among the particles this thread looks at
+        for (uint32_t j = tid; j < n; j += blockDim.x)
             {
-            const double4* src = reinterpret_cast<const double4*>(frame) + base;
-            for (uint32_t j = tid; j < n; j += blockDim.x)
-                {
-                const double4 r = ld256_stream(src + j);
-                sx[j] = r.x;
-                sy[j] = r.y;
-                sz[j] = r.z;
-                mx = max(mx, max(max(abs_hi(r.x), abs_hi(r.y)), abs_hi(r.z)));
-                }
-            }
-        else if (stride == RHOK_F32)
-            {
-            // float32 xyz, the way GSD stores positions: widened exactly, as NumPy does in np.dot(f32, f64)
-            const float* src = reinterpret_cast<const float*>(pos) + (unsigned long long)t * frame_stride + 3ull * base;
-            for (uint32_t e = tid; e < 3 * n; e += blockDim.x)
-                {
-                const double v = (double)__ldg(src + e);
-                const uint32_t j = e / 3, c = e - 3 * j;
-                (c == 0 ? sx : (c == 1 ? sy : sz))[j] = v;
-                mx = max(mx, abs_hi(v));
-                }
-            }
-        else
-            {
-            const double* src = frame + 3ull * base;
-            for (uint32_t e = tid; e < 3 * n; e += blockDim.x)
-                {
-                const double v = __ldg(src + e);
-                const uint32_t j = e / 3, c = e - 3 * j;
-                (c == 0 ? sx : (c == 1 ? sy : sz))[j] = v;
-                mx = max(mx, abs_hi(v));
-                }
+            const double4 r = buf[j];
+            mx = max(mx, max(max(abs_hi(r.x), abs_hi(r.y)), abs_hi(r.z)));
             }
         mx = __reduce_max_sync(0xffffffffu, mx);
         if ((tid & 31u) == 0)
-            atomicMax(&tile_maxhi[tile & 1u], mx);
+            atomicMax(&tile_maxhi[cur], mx);
         __syncthreads();
         // upper bound of |coordinate| over the tile (hi word + 1, lo word 0 bounds every double with that hi word); with
         // the thread's own bound on |kx| + |ky| + |kz| it decides once per tile whether any argument can reach 2^20
-        const unsigned int mh = tile_maxhi[tile & 1u];
+        const unsigned int mh = tile_maxhi[cur];
         if (tid == 0)
-            tile_maxhi[(tile + 1u) & 1u] = 0u;
+            tile_maxhi[cur ^ 1u] = 0u;
         const bool fast = mh < 0x7ff00000u && __dmul_rn(kbound, __hiloint2double((int)(mh + 1u), 0)) < 1048575.0;
         if (active)
             {
             if (fast)
-                rhok_walk<KB, false>(sx, sy, sz, tab, lane_slot, pg, n, groups, kx, ky, kz, re, im);
+                rhok_walk<KB, false>(buf, tab, lane_slot, pg, n, groups, kx, ky, kz, re, im);
             else
-                rhok_walk<KB, true>(sx, sy, sz, tab, lane_slot, pg, n, groups, kx, ky, kz, re, im);
+                rhok_walk<KB, true>(buf, tab, lane_slot, pg, n, groups, kx, ky, kz, re, im);
             }
         }
+    __syncthreads(); // the tile buffers become the fold area
 
     // fold the particle groups (fixed order)
     const uint32_t KP = KQ * KB;
@@ -369,7 +402,7 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
         CAVB_CHECK(cudaMalloc((void**)&h->rhok_table, sizeof(host_tab)));
         CAVB_CHECK(cudaMemcpy(h->rhok_table, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice));
         CAVB_CHECK(cudaFuncSetAttribute(k_rhok<RHOK_KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(double2) * RHOK_TAB * RHOK_REP + sizeof(double) * 2 * 256 * RHOK_KB)));
+                                        (int)(sizeof(double2) * RHOK_TAB * RHOK_REP + sizeof(double4) * 2 * RHOK_TILE)));
         }
     // two CTAs of 256 threads per SM: the 64 KB table of each leaves no room for four of 128 (which were worth 1-2 % when
     // the table was four entries: a CTA staging its next tile idled a quarter of the SM's warps instead of half)
@@ -407,7 +440,9 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
         const uint32_t Ks = (K - k0) < (uint32_t)threads * KB ? (K - k0) : (uint32_t)threads * KB;
         const uint32_t KQ = (Ks + KB - 1) / KB;
         const uint32_t groups = (uint32_t)threads / KQ;
-        const size_t smem = sizeof(double2) * RHOK_TAB * RHOK_REP + sizeof(double) * 2 * groups * KQ * KB;
+        // table | two tile buffers (32 KB; the fold of the particle groups reuses them: 2 * groups * KQ * KB doubles <= 16 KB)
+        const size_t smem = sizeof(double2) * RHOK_TAB * RHOK_REP + sizeof(double4) * 2 * RHOK_TILE;
+        (void)groups;
         k_rhok<KB><<<dim3(P, T), threads, smem, s>>>(pos, stride, frame_stride, N, kvec, k0, Ks, K, target, P, direct,
                                                      (const double2*)h->rhok_table);
         CAVB_CHECK(cudaGetLastError());
