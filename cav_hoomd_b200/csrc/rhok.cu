@@ -22,6 +22,9 @@ namespace cavb
 #ifndef RHOK_KB
 #define RHOK_KB 4
 #endif
+#ifndef RHOK_CTA
+#define RHOK_CTA 256 // largest (and default) CTA size
+#endif
 constexpr int RHOK_KB_HOST = RHOK_KB;
 constexpr int RHOK_TILE = 512;  // particles per shared-memory tile (16 KB as double4; two buffers)
 constexpr uint32_t RHOK_F32 = 13;  // internal `stride` code: float32 xyz positions (frame_stride then counts floats)
@@ -180,8 +183,10 @@ __device__ __forceinline__ void rhok_stage(double4* dst, const double* pos, uint
 // Two tile buffers: the copy of tile i+1 is issued before tile i is walked, so no warp ever waits for HBM -- with two
 // CTAs of eight warps per SM, a CTA that stopped to stage its next tile left the FP64 pipe to the other CTA's two warps
 // per scheduler, which cannot keep it busy.
-template<int KB>
-__global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
+// F32: the instantiation for float32 positions (its six prefetch registers cost the double instantiation 3.7 % when
+// both lived in one kernel: 0.0809 -> 0.0839 ms per frame).
+template<int KB, bool F32>
+__global__ void __launch_bounds__(RHOK_CTA, RHOK_MIN_CTAS)
     k_rhok(const double* __restrict__ pos, uint32_t stride, unsigned long long frame_stride, uint32_t N,
            const double* __restrict__ kvec, uint32_t k0, uint32_t Ks, uint32_t K, double* __restrict__ out, uint32_t P,
            int direct, const double2* __restrict__ table)
@@ -231,6 +236,9 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
     const char* tab = reinterpret_cast<const char*>(stab);
     const uint32_t lane_slot = (tid & (RHOK_REP - 1)) * 16u;
 
+    constexpr int RHOK_PF = 3 * RHOK_TILE / 256; // floats of a tile per thread of a 256-thread CTA
+    float pf[RHOK_PF]; // (dead in the double instantiation)
+    const bool pre32 = F32 && blockDim.x * (uint32_t)RHOK_PF >= 3u * RHOK_TILE;
     for (uint32_t tile = tile_lo; tile < tile_hi; tile++)
         {
         const uint32_t cur = (tile - tile_lo) & 1u;
@@ -238,9 +246,32 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
         const uint32_t n = min((uint32_t)RHOK_TILE, N - tile * RHOK_TILE);
         cp_async_wait_all();
         __syncthreads(); // this tile has landed (and the table, first time); everyone has left the other buffer
-        if (tile + 1 < tile_hi)
-            rhok_stage(tiles2 + (cur ^ 1u) * RHOK_TILE, pos, stride, frame_off, (tile + 1) * RHOK_TILE,
-                       min((uint32_t)RHOK_TILE, N - (tile + 1) * RHOK_TILE), tid, blockDim.x);
+        uint32_t n_next = 0u;
+        if constexpr (!F32)
+            {
+            if (tile + 1 < tile_hi)
+                rhok_stage(tiles2 + (cur ^ 1u) * RHOK_TILE, pos, stride, frame_off, (tile + 1) * RHOK_TILE,
+                           min((uint32_t)RHOK_TILE, N - (tile + 1) * RHOK_TILE), tid, blockDim.x);
+            }
+        else
+            {
+            n_next = tile + 1 < tile_hi ? min((uint32_t)RHOK_TILE, N - (tile + 1) * RHOK_TILE) : 0u;
+            if (pre32)
+                {
+                // float32 positions cannot be copied asynchronously (they are widened on the way): this thread's six
+                // floats of the next tile wait in registers while this tile is walked
+                const float* src = reinterpret_cast<const float*>(pos) + frame_off + 3ull * (tile + 1) * RHOK_TILE;
+#pragma unroll
+                for (int i = 0; i < RHOK_PF; i++)
+                    {
+                    const uint32_t e = tid + i * blockDim.x;
+                    pf[i] = e < 3 * n_next ? __ldg(src + e) : 0.0f;
+                    }
+                }
+            else if (n_next)
+                rhok_stage(tiles2 + (cur ^ 1u) * RHOK_TILE, pos, stride, frame_off, (tile + 1) * RHOK_TILE, n_next, tid,
+                           blockDim.x);
+            }
         unsigned int mx = 0u; // largest hi word of |coordinate| among the particles this thread looks at
         for (uint32_t j = tid; j < n; j += blockDim.x)
             {
@@ -263,6 +294,21 @@ __global__ void __launch_bounds__(256, RHOK_MIN_CTAS)
                 rhok_walk<KB, false>(buf, tab, lane_slot, pg, n, groups, kx, ky, kz, re, im);
             else
                 rhok_walk<KB, true>(buf, tab, lane_slot, pg, n, groups, kx, ky, kz, re, im);
+            }
+        if constexpr (F32)
+            {
+            if (pre32)
+                {
+                double* d1 = reinterpret_cast<double*>(tiles2 + (cur ^ 1u) * RHOK_TILE); // nobody reads this buffer now
+#pragma unroll
+                for (int i = 0; i < RHOK_PF; i++)
+                    {
+                    const uint32_t e = tid + i * blockDim.x;
+                    const uint32_t j = e / 3, c = e - 3 * j;
+                    if (e < 3 * n_next)
+                        d1[4 * j + c] = (double)pf[i];
+                    }
+                }
             }
         }
     __syncthreads(); // the tile buffers become the fold area
@@ -401,12 +447,15 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
         rhok_table_host(host_tab);
         CAVB_CHECK(cudaMalloc((void**)&h->rhok_table, sizeof(host_tab)));
         CAVB_CHECK(cudaMemcpy(h->rhok_table, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice));
-        CAVB_CHECK(cudaFuncSetAttribute(k_rhok<RHOK_KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(double2) * RHOK_TAB * RHOK_REP + sizeof(double4) * 2 * RHOK_TILE)));
+        const int smem_max = (int)(sizeof(double2) * RHOK_TAB * RHOK_REP + sizeof(double4) * 2 * RHOK_TILE);
+        CAVB_CHECK(cudaFuncSetAttribute(k_rhok<RHOK_KB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CAVB_CHECK(cudaFuncSetAttribute(k_rhok<RHOK_KB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         }
     // two CTAs of 256 threads per SM: the 64 KB table of each leaves no room for four of 128 (which were worth 1-2 % when
     // the table was four entries: a CTA staging its next tile idled a quarter of the SM's warps instead of half)
-    const int threads = (h->tune.rhok_threads == 128 || h->tune.rhok_threads == 256) ? h->tune.rhok_threads : 256;
+    const int threads = (h->tune.rhok_threads >= 128 && h->tune.rhok_threads <= RHOK_CTA && h->tune.rhok_threads % 128 == 0)
+                            ? h->tune.rhok_threads
+                            : RHOK_CTA;
     const uint32_t tiles = (N + RHOK_TILE - 1) / RHOK_TILE;
     uint32_t P = (24u * (uint32_t)h->num_sms + T - 1) / T;
     if (P > tiles)
@@ -443,8 +492,12 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
         // table | two tile buffers (32 KB; the fold of the particle groups reuses them: 2 * groups * KQ * KB doubles <= 16 KB)
         const size_t smem = sizeof(double2) * RHOK_TAB * RHOK_REP + sizeof(double4) * 2 * RHOK_TILE;
         (void)groups;
-        k_rhok<KB><<<dim3(P, T), threads, smem, s>>>(pos, stride, frame_stride, N, kvec, k0, Ks, K, target, P, direct,
-                                                     (const double2*)h->rhok_table);
+        if (stride == RHOK_F32)
+            k_rhok<KB, true><<<dim3(P, T), threads, smem, s>>>(pos, stride, frame_stride, N, kvec, k0, Ks, K, target, P, direct,
+                                                               (const double2*)h->rhok_table);
+        else
+            k_rhok<KB, false><<<dim3(P, T), threads, smem, s>>>(pos, stride, frame_stride, N, kvec, k0, Ks, K, target, P, direct,
+                                                                (const double2*)h->rhok_table);
         CAVB_CHECK(cudaGetLastError());
         h->launches += 1;
         }
