@@ -98,9 +98,8 @@ __device__ __forceinline__ void rhok_walk(const double4* tile, const char* tab, 
         if (!CHECK || !huge)
             {
             // one basic block for the KB independent chains: coefficients are fetched once
-            // (written stage by stage over the KB arguments instead -- every dependent pair 2 KB instructions apart in
-            // program order -- ptxas interleaves three or four chains instead of two or three, needs 40 B of spills
-            // and the frame takes 0.1277 ms instead of 0.1256: not what limits the FP64 pipe at 70 %)
+            // (tried and dropped: the chains written stage by stage -- spills; the next particle's arguments formed
+            // beside the chains of this one, a software pipeline -- 124 registers, 0.0816 ms per frame against 0.0810)
 #pragma unroll
             for (int m = 0; m < KB; m++)
                 {
