@@ -492,7 +492,7 @@ def leg_fkt(cx, n_mol):
         "ms_origin_lag_table_1000x1000": ms_corr,
         "position_GBs": 32 * N / (ms_per_frame * 1e-3) / 1e9,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tflops, "traffic": None, "kernel": "k_rhok<4>",
+                     "frac": achieved / peak_tflops, "traffic": None, "kernel": "k_rhok<4, false>",
                      "convention": f"FP64-pipe issue slots, counted as fused multiply-adds (2 flops each): {FP64_PER_PAIR} "
                                    f"FP64 instructions per (particle, k) pair (3 for k.r, 4 reduction to |r| <= pi/512, 6 for sin r and cos r, 4 rotate-by-table-entry-and-accumulate; round 1 and early round 2 needed 26); arithmetic flops are {FLOPS_PER_PAIR} per pair",
                      "arithmetic_TFLOPs": FLOPS_PER_PAIR * pairs_per_s / cx.world / 1e12,
