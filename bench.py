@@ -342,7 +342,7 @@ def run_reference(args):
         "e2e": {"value": out["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line))
+    _LINES.append(json.dumps(line))
     return 0
 
 
@@ -1044,7 +1044,7 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = min(os.cpu_count() or 1, 32)
         line["cpu_baseline"] = cpu_reference_throughput(n_mol, args.cpu_steps, cores)
-    print(json.dumps(line))
+    _LINES.append(json.dumps(line))
     return 0
 
 
@@ -1066,9 +1066,24 @@ def main():
     ap.add_argument("--no-sharded", action="store_true")
     ap.add_argument("--no-small-n", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    # stdout carries the ONE JSON line and nothing else: native libraries write there too (NCCL prints its version
+    # banner to fd 1 when the sharded leg creates its communicator), so fd 1 points at stderr while the run lasts and
+    # the line goes to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return (run_reference if args.impl == "reference" else run_b200)(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        for text in _LINES:
+            print(text)
+        sys.stdout.flush()
+
+
+_LINES = []  # what main() prints on the real stdout
 
 
 if __name__ == "__main__":
