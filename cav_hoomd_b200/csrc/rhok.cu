@@ -4,13 +4,13 @@
 // Batched form of compute_density_field / compute_field_autocorr
 // (reference src/cavitymd/analysis.py:34-47, :359-364), which loops over k in Python and makes K
 // NumPy passes over N every step.  Here one launch covers T frames x K wavevectors:
-//   grid (P, T): CTA (p, t) owns a contiguous slice of frame t's particles; a tile of positions is
-//   staged in shared memory (coalesced, stride 3 or 4 -> xyz); thread (group, k) keeps rho_k's
-//   (re, im) in registers and walks the tile's particles group, group+G, ... (broadcast LDS);
-//   groups are folded in shared memory; slices are folded by a second tiny kernel in slice order.
-// The sum order is fixed, so results are bitwise reproducible.  The work is FP64 sincos bound
-// (about 50 fp64 instructions per (particle, k) pair against 24/K bytes), not HBM bound, and the
-// contraction is only k x 3 deep: no tensor-core shape here (BASELINE.json north_star (3)).
+//   grid (P, T): CTA (p, t) owns a contiguous slice of frame t's particles; tiles of positions are
+//   copied into shared memory one tile ahead (cp.async, two buffers); thread (group, k-quad) keeps
+//   four rho_k's (re, im) in registers and walks the tile's particles group, group+G, ... (broadcast
+//   LDS); groups are folded in shared memory; slices are folded by a second tiny kernel in slice order.
+// The sum order is fixed, so results are bitwise reproducible.  The work is FP64 bound (17 fp64
+// instructions per (particle, k) pair against 24/K bytes), not HBM bound, and the contraction is
+// only k x 3 deep: no tensor-core shape here (BASELINE.json north_star (3)).
 #include "cavb200_internal.cuh"
 
 namespace cavb
