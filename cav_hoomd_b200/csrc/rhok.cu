@@ -22,6 +22,9 @@ namespace cavb
 #ifndef RHOK_KB
 #define RHOK_KB 4
 #endif
+#ifndef RHOK_GRID_PER_SM
+#define RHOK_GRID_PER_SM 24 // most CTAs of a launch per resident slot (rhok_slices picks the count)
+#endif
 #ifndef RHOK_CTA
 #define RHOK_CTA 256 // largest (and default) CTA size
 #endif
@@ -420,6 +423,34 @@ static void rhok_table_host(double2* tab)
         }
     }
 
+// How many slices P a frame is cut into.  The CTAs of a launch do equal work and two are resident per SM, so they run
+// in waves: the launch takes ceil(P T / slots) waves of ceil(tiles / P) tiles each, plus a fixed cost per CTA (table
+// fill, fold: about a quarter of a tile).  A fixed 24 CTAs per SM lost 2-4 % to a ragged last wave or a ragged last
+// tile count (1M particles: 32 frames P = 111 -> 12 waves x 18 tiles = 216 tile times against 211.2 ideal, P = 37 -> 4 x
+// 53 = 212; 8 frames: P = 444 -> 12 x 5 = 60 against 52.8, P = 222 -> 6 x 9 = 54; profiles/fkt_r2c.txt).
+static uint32_t rhok_slices(uint32_t tiles, uint32_t T, uint32_t slots)
+    {
+    uint32_t pmax = (uint32_t)(((uint64_t)RHOK_GRID_PER_SM * slots + T - 1) / T);
+    if (pmax > tiles)
+        pmax = tiles;
+    if (pmax < 1)
+        pmax = 1;
+    uint32_t best = 1;
+    double best_cost = 0.0;
+    for (uint32_t P = 1; P <= pmax; P++)
+        {
+        const uint64_t waves = ((uint64_t)P * T + slots - 1) / slots;
+        const uint32_t per = (tiles + P - 1) / P;
+        const double cost = (double)waves * ((double)per + 0.25);
+        if (P == 1 || cost < best_cost)
+            {
+            best = P;
+            best_cost = cost;
+            }
+        }
+    return best;
+    }
+
 static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, uint64_t frame_stride, uint32_t N,
                        uint32_t T, const double* kvec, uint32_t K, double* rho, void* stream)
     {
@@ -456,11 +487,7 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
                             ? h->tune.rhok_threads
                             : RHOK_CTA;
     const uint32_t tiles = (N + RHOK_TILE - 1) / RHOK_TILE;
-    uint32_t P = (24u * (uint32_t)h->num_sms + T - 1) / T;
-    if (P > tiles)
-        P = tiles;
-    if (P < 1)
-        P = 1;
+    const uint32_t P = rhok_slices(tiles, T, 2u * (uint32_t)h->num_sms);
     const int direct = (P == 1);
     double* target = rho;
     if (!direct)
