@@ -211,3 +211,35 @@ def test_sincos_table_cell_edges(handle):
     assert float(err_c) <= 2.3e-16 and float(err_s) <= 2.3e-16, (float(err_c), float(err_s))
     # exp(-ix) is the conjugate of exp(ix) bit for bit: the table is built by octant symmetry and rint() is odd
     assert np.array_equal(rho[:, 0, 0], rho[:, 1, 0]) and np.array_equal(rho[:, 0, 1], -rho[:, 1, 1])
+
+
+@pytest.mark.parametrize("N", [511, 512, 513, 1537])
+def test_rhok_many_frames_one_slice_per_frame(handle, N):
+    """Thousands of frames in one launch make the grid rule cut a frame into ONE slice (rhok_slices: whole waves of
+    resident CTAs), so a CTA walks all tiles of its frame through both tile buffers, ragged last tile included, and
+    writes rho directly (no fold kernel) -- for the three position layouts, against the NumPy restatement."""
+    T, K = 3000, 5
+    rng = np.random.default_rng(N)
+    pos32 = rng.uniform(-30, 30, size=(T, N, 3)).astype(np.float32)
+    pos = pos32.astype(np.float64)
+    kvec = O.numpy_fibonacci_sphere(8)[:K] * 1.1
+    d_k = capi.DeviceArray.from_numpy(kvec)
+    ref = np.exp(1j * np.einsum("tnc,kc->tkn", pos, kvec)).sum(axis=2)
+    out = {}
+    for name in ("xyz", "scalar4", "f32"):
+        d_rho = capi.DeviceArray((T, K, 2), np.float64)
+        d_rho.fill_bytes(0xFF)
+        if name == "xyz":
+            handle.rhok(capi.DeviceArray.from_numpy(pos), 3, 3 * N, N, T, d_k, K, d_rho)
+        elif name == "scalar4":
+            p4 = np.full((T, N, 4), np.nan)  # the fourth word (type bits) must never be looked at
+            p4[:, :, :3] = pos
+            handle.rhok(capi.DeviceArray.from_numpy(p4), 4, 4 * N, N, T, d_k, K, d_rho)
+        else:
+            handle.rhok_f32(capi.DeviceArray.from_numpy(pos32), 3 * N, N, T, d_k, K, d_rho)
+        r = d_rho.numpy()
+        out[name] = r
+        assert np.abs((r[..., 0] + 1j * r[..., 1]) - ref).max() <= 1e-13 * N + 1e-12
+    # same values, same walk order: the three layouts agree bit for bit
+    assert np.array_equal(out["xyz"].view(np.uint64), out["scalar4"].view(np.uint64))
+    assert np.array_equal(out["xyz"].view(np.uint64), out["f32"].view(np.uint64))
