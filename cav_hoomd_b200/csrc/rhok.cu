@@ -102,7 +102,8 @@ __device__ __forceinline__ void rhok_walk(const double4* tile, const char* tab, 
             {
             // one basic block for the KB independent chains: coefficients are fetched once
             // (tried and dropped: the chains written stage by stage -- spills; the next particle's arguments formed
-            // beside the chains of this one, a software pipeline -- 124 registers, 0.0816 ms per frame against 0.0810)
+            // beside the chains of this one, a software pipeline -- 124 registers, 0.0816 ms per frame against 0.0810; only
+            // the next particle's coordinates loaded an iteration ahead -- 0.0828 against 0.0794)
 #pragma unroll
             for (int m = 0; m < KB; m++)
                 {
