@@ -29,7 +29,10 @@ namespace cavb
 #define RHOK_CTA 256 // largest (and default) CTA size
 #endif
 constexpr int RHOK_KB_HOST = RHOK_KB;
-constexpr int RHOK_TILE = 512;  // particles per shared-memory tile (16 KB as double4; two buffers)
+#ifndef RHOK_TILE_N
+#define RHOK_TILE_N 512
+#endif
+constexpr int RHOK_TILE = RHOK_TILE_N;  // particles per shared-memory tile (16 KB as double4; two buffers)
 constexpr uint32_t RHOK_F32 = 13;  // internal `stride` code: float32 xyz positions (frame_stride then counts floats)
 
 // exp(i x) for |x| < 2^20 by table and short polynomial, both components to ~1 ulp of 1 (abs. error <= 2.4e-16).
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(RHOK_CTA, RHOK_MIN_CTAS)
     const char* tab = reinterpret_cast<const char*>(stab);
     const uint32_t lane_slot = (tid & (RHOK_REP - 1)) * 16u;
 
-    constexpr int RHOK_PF = 3 * RHOK_TILE / 256; // floats of a tile per thread of a 256-thread CTA
+    constexpr int RHOK_PF = (3 * RHOK_TILE + 255) / 256; // floats of a tile per thread of a 256-thread CTA
     float pf[RHOK_PF]; // (dead in the double instantiation)
     const bool pre32 = F32 && blockDim.x * (uint32_t)RHOK_PF >= 3u * RHOK_TILE;
     for (uint32_t tile = tile_lo; tile < tile_hi; tile++)
