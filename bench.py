@@ -460,16 +460,18 @@ def leg_fkt(cx, n_mol):
     bufs = [capi.DeviceArray.from_numpy(frames) for _ in range(2)]  # 2 x 1 GB
     d_rho = capi.DeviceArray((T, K, 2), np.float64)
 
+    # one GPU: 4 launches of T frames (128 frames); N GPUs: the 1000 frames in equal contiguous ranges per rank
+    # (replicas.frames_for_rank, balanced), launches of at most T frames, no data-path collective, time = max over ranks
+    from cav_hoomd_b200 import replicas
+    blocks = [(0, T)] * 4 if cx.world == 1 else replicas.frames_for_rank(ORIGINS, cx.rank, cx.world, block=T, balanced=True)
+
     def launch(k):
-        h.rhok(bufs[k & 1], 4, N * 4, N, T, d_k, K, d_rho, st)
+        h.rhok(bufs[k & 1], 4, N * 4, N, blocks[k % len(blocks)][1], d_k, K, d_rho, st)
 
     for k in range(3):
         launch(k)
     capi.sync()
-    # one GPU: 4 launches (128 frames); N GPUs: the 1000 frames in blocks of T round-robin over the ranks
-    # (replicas.frames_for_rank), no data-path collective, time = max over ranks
-    from cav_hoomd_b200 import replicas
-    n_launch = 4 if cx.world == 1 else len(replicas.frames_for_rank(ORIGINS, cx.rank, cx.world, block=T))
+    n_launch = len(blocks)
     ms, launches = cx.timed(launch, n_launch, gate=True)
     frames_done = n_launch * T if cx.world == 1 else ORIGINS
     ms_per_frame = ms / frames_done
@@ -500,7 +502,7 @@ def leg_fkt(cx, n_mol):
                                     "cav_hoomd_b200/csrc/debug.cu), best of 4"},
     }
     if cx.world > 1:
-        out["multi_gpu"] = {"n_gpus": cx.world, "partition": f"blocks of {T} frames round-robin over ranks, no collective in the data path",
+        out["multi_gpu"] = {"n_gpus": cx.world, "partition": f"equal contiguous ranges of frames per rank in launches of at most {T}, no collective in the data path",
                             "seconds_for_1000_frame_field_sum": ms * 1e-3, "pairs_per_s": N * K * ORIGINS / (ms * 1e-3)}
     for b in bufs:
         b.free()

@@ -164,3 +164,13 @@ def test_frames_for_rank_covers_every_frame_once():
                     assert 0 < count <= 16
                     seen.extend(range(first, first + count))
             assert sorted(seen) == list(range(T))
+            # balanced: contiguous ranges whose sizes differ by at most one frame
+            seen, sizes = [], []
+            for r in range(world):
+                mine = replicas.frames_for_rank(T, r, world, block=16, balanced=True)
+                assert all(0 < c <= 16 for _, c in mine)
+                frames = [f for first, c in mine for f in range(first, first + c)]
+                assert frames == list(range(frames[0], frames[0] + len(frames))) if frames else True
+                sizes.append(len(frames))
+                seen.extend(frames)
+            assert sorted(seen) == list(range(T)) and max(sizes) - min(sizes) <= 1
