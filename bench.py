@@ -477,6 +477,19 @@ def leg_fkt(cx, n_mol):
     ms_per_frame = ms / frames_done
     pairs_per_s = N * K / (ms_per_frame * 1e-3)
     rho = d_rho.numpy(st)
+    # the tracker's live use (reference analysis.py:34-47 called once per sampling period inside a run): one frame per
+    # call, each call on a different frame of the rotating buffers
+    d_rho1 = capi.DeviceArray((1, K, 2), np.float64)
+
+    def launch_one(k):
+        h.rhok(bufs[k & 1].ptr + (k % T) * N * 32, 4, N * 4, N, 1, d_k, K, d_rho1, st)
+
+    live = None
+    if cx.world == 1:
+        for k in range(3):
+            launch_one(k)
+        ms_live, _ = cx.timed(launch_one, 16, gate=True)
+        live = {"ms_per_call": ms_live / 16, "note": "T = 1: one 1M-particle frame x 64 wave vectors per call (k_rhok + k_rhok_fold), 16 calls back to back"}
     big = np.ascontiguousarray(np.tile(rho, (ORIGINS // T + 1, 1, 1))[:ORIGINS])
     d_big = capi.DeviceArray.from_numpy(big)
     d_F = capi.DeviceArray((ORIGINS, ORIGINS), np.float64)
@@ -490,6 +503,7 @@ def leg_fkt(cx, n_mol):
         "workload": f"F(k,t): {N} particles x {K} wave vectors per frame, {ORIGINS} time origins (BASELINE configs[4]); "
                     f"{T} frames per launch, float64 Scalar4 positions resident in HBM (2 rotating buffers x {frames.nbytes >> 20} MB)",
         "ms_per_frame": ms_per_frame, "pairs_per_s": pairs_per_s, "frames_timed": frames_done, "gpu_launches": launches,
+        "live_single_frame": live,
         "seconds_for_1000_origins": ms_per_frame * 1e-3 * ORIGINS * (1 if cx.world == 1 else 1) + ms_corr * 1e-3,
         "ms_origin_lag_table_1000x1000": ms_corr,
         "position_GBs": 32 * N / (ms_per_frame * 1e-3) / 1e9,

@@ -215,6 +215,13 @@ __global__ void __launch_bounds__(RHOK_CTA, RHOK_MIN_CTAS)
     const uint32_t tile_lo = p * tiles_per;
     const uint32_t tile_hi = min(tiles, tile_lo + tiles_per);
     const unsigned long long frame_off = (unsigned long long)t * frame_stride;
+
+    // every copy of a table entry is written by one thread: consecutive threads write consecutive 16-byte slots.
+    // Programmatic dependent launch: the table (handle-owned, constant) may be read while the previous kernel of the
+    // stream is still draining; positions, wave vectors and the partial sums may not be touched before pdl_wait()
+    for (uint32_t e = tid; e < RHOK_TAB * RHOK_REP; e += blockDim.x)
+        stab[e] = __ldg(table + e / RHOK_REP);
+    pdl_wait();
     if (tile_lo < tile_hi)
         rhok_stage(tiles2, pos, stride, frame_off, tile_lo * RHOK_TILE, min((uint32_t)RHOK_TILE, N - tile_lo * RHOK_TILE), tid,
                    blockDim.x);
@@ -236,9 +243,6 @@ __global__ void __launch_bounds__(RHOK_CTA, RHOK_MIN_CTAS)
         kbound = fmax(kbound, fabs(kx[m]) + fabs(ky[m]) + fabs(kz[m]));
     if (tid < 2)
         tile_maxhi[tid] = 0u;
-    // every copy of an entry is written by one thread: consecutive threads write consecutive 16-byte slots
-    for (uint32_t e = tid; e < RHOK_TAB * RHOK_REP; e += blockDim.x)
-        stab[e] = __ldg(table + e / RHOK_REP);
     const char* tab = reinterpret_cast<const char*>(stab);
     const uint32_t lane_slot = (tid & (RHOK_REP - 1)) * 16u;
 
@@ -317,6 +321,7 @@ __global__ void __launch_bounds__(RHOK_CTA, RHOK_MIN_CTAS)
                 }
             }
         }
+    pdl_launch_dependents(); // the fold kernel's (or the next call's) CTAs may take the SMs this grid's CTAs leave
     __syncthreads(); // the tile buffers become the fold area
 
     // fold the particle groups (fixed order)
@@ -351,6 +356,8 @@ __global__ void k_rhok_fold(const double* __restrict__ part, uint32_t P, uint32_
     {
     const unsigned long long e = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // (t, k) pair
     const uint32_t lane = threadIdx.x & 31;
+    pdl_wait(); // launched while k_rhok was draining
+    pdl_launch_dependents();
     if (e >= (unsigned long long)T * K)
         return;
     const unsigned long long t = e / K, k = e % K;
@@ -509,6 +516,9 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
             }
         target = h->rhok_partials;
         }
+    cudaLaunchAttribute pdl_attr;
+    pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr.val.programmaticStreamSerializationAllowed = 1;
     // wave vectors in slabs of at most threads*KB = 1024 (one launch for the usual K); KB = 4 k per thread
 #ifndef RHOK_KB
 #define RHOK_KB 4
@@ -522,20 +532,34 @@ static int rhok_launch(cavb200_handle* h, const double* pos, uint32_t stride, ui
         // table | two tile buffers (32 KB; the fold of the particle groups reuses them: 2 * groups * KQ * KB doubles <= 16 KB)
         const size_t smem = sizeof(double2) * RHOK_TAB * RHOK_REP + sizeof(double4) * 2 * RHOK_TILE;
         (void)groups;
-        if (stride == RHOK_F32)
-            k_rhok<KB, true><<<dim3(P, T), threads, smem, s>>>(pos, stride, frame_stride, N, kvec, k0, Ks, K, target, P, direct,
-                                                               (const double2*)h->rhok_table);
-        else
-            k_rhok<KB, false><<<dim3(P, T), threads, smem, s>>>(pos, stride, frame_stride, N, kvec, k0, Ks, K, target, P, direct,
-                                                                (const double2*)h->rhok_table);
-        CAVB_CHECK(cudaGetLastError());
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(P, T);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cfg.attrs = &pdl_attr;
+        cfg.numAttrs = h->tune.pdl ? 1 : 0;
+        unsigned long long fs = frame_stride;
+        const double2* tabp = (const double2*)h->rhok_table;
+        int direct_i = direct;
+        void* args[] = {(void*)&pos, (void*)&stride, (void*)&fs,    (void*)&N, (void*)&kvec,     (void*)&k0,
+                        (void*)&Ks,  (void*)&K,      (void*)&target, (void*)&P, (void*)&direct_i, (void*)&tabp};
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, stride == RHOK_F32 ? (const void*)k_rhok<KB, true> : (const void*)k_rhok<KB, false>,
+                                       args));
         h->launches += 1;
         }
     if (!direct)
         {
         const unsigned long long pairs = (unsigned long long)T * K;
-        k_rhok_fold<<<(unsigned int)((pairs * 32 + 255) / 256), 256, 0, s>>>(target, P, K, T, rho);
-        CAVB_CHECK(cudaGetLastError());
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned int)((pairs * 32 + 255) / 256));
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cfg.attrs = &pdl_attr;
+        cfg.numAttrs = h->tune.pdl ? 1 : 0;
+        const double* part = target;
+        void* args[] = {(void*)&part, (void*)&P, (void*)&K, (void*)&T, (void*)&rho};
+        CAVB_CHECK(cudaLaunchKernelExC(&cfg, (const void*)k_rhok_fold, args));
         h->launches += 1;
         }
     return 0;
